@@ -1,0 +1,798 @@
+// bf_cuda.cu -- kernels + C ABI (include/bf_cuda.h) of the B200-native motion-compensation path.
+//
+// One persistent cooperative kernel runs OptimizerRolling::run() (optimizer_rolling.h:48-125) for a
+// whole batch of independent slices: the grid is cut into groups of G CTAs, each group pulls
+// slices from a queue and iterates   event pass -> barrier -> image pass -> barrier -> GD update
+// entirely on the device; no host round trip per iteration.  See DESIGN.md.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bf_device.cuh"
+
+// =================================================================================================
+// Kernels
+// =================================================================================================
+
+struct __align__(16) Smem {
+    u64 p0[BF_PTILE_MAX_ELEMS];
+    u64 p1[BF_PTILE_MAX_ELEMS];
+    float a[BF_AR * BF_AC];
+    double red[(BF_NT / 32) * BF_NSUMS];
+    SliceDesc sd;
+    BfGeom g;
+    BfPack pk;
+    BfProj proj;
+    BfOpt opt;
+    int cont;
+    int slice;
+    int minmax[6];
+};
+
+template <int SH>
+__device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank) {
+    u64 *img0 = P.images + (size_t)group * 2 * P.img_elems;
+    u64 *img1 = img0 + P.img_elems;
+    double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
+    const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
+
+    if (threadIdx.x == 0) {
+        bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
+        if (S.sd.has_init) {
+            // set_model (optimizer_rolling.h:289-299): note model.cx/cy are used as stored
+            const bf_model &m = S.sd.init;
+            bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
+        }
+    }
+    __syncthreads();
+
+    int buf = 0;
+    for (int iter = 0;; ++iter) {
+        u64 *img_new = buf ? img1 : img0;
+        u64 *img_old = buf ? img0 : img1;
+        event_pass(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new,
+                   iter > 0 ? img_old : nullptr, nullptr);
+        group_barrier(&ws->bar, bar_target, P.G);   // A: all splats of this iteration are in L2
+
+        Acc acc;
+        acc_zero(acc);
+        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, rank, P.G, S.p0, S.p1, S.a, nullptr, nullptr, nullptr);
+        acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
+        group_barrier(&ws->bar, bar_target, P.G);   // B: all partial sums are visible
+
+        if (threadIdx.x < 32) {
+            BfSums s;
+            group_sums(s, partials, P.G);
+            if (threadIdx.x == 0)
+                S.cont = bf_opt_advance(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!S.cont) break;
+        buf ^= 1;
+    }
+    // Last re-projection of iteration_step (optimizer_rolling.h:340-344) + clearing of the live image.
+    event_pass(P, S.sd, S.g, S.pk, S.proj, rank, false, P.want_events != 0, nullptr, buf ? img1 : img0,
+               P.want_events ? P.nxy : nullptr);
+}
+
+__global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int group = blockIdx.x / P.G;
+    const int rank = blockIdx.x - group * P.G;
+    GroupWs *ws = P.ws + group;
+    unsigned bar_target = 0;
+    int parity = 0;
+
+    for (;;) {
+        // ---- fetch the next slice for this group ------------------------------------------------
+        if (rank == 0 && threadIdx.x == 0) {
+            const int s = atomicAdd(P.queue, 1);
+            int *bb = ws->bbox[parity];
+            bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; bb[4] = INT_MAX; bb[5] = INT_MIN;
+            ws->cur_slice = s;
+        }
+        group_barrier(&ws->bar, bar_target, P.G);
+        const int slice = __ldcg(&ws->cur_slice);
+        if (slice >= P.n_slices) break;
+        if (threadIdx.x == 0) {
+            S.sd = P.slices[slice];
+            S.minmax[0] = INT_MAX; S.minmax[1] = INT_MIN; S.minmax[2] = INT_MAX;
+            S.minmax[3] = INT_MIN; S.minmax[4] = INT_MAX; S.minmax[5] = INT_MIN;
+        }
+        __syncthreads();
+
+        // ---- bbox over fr_x / fr_y (optimizer_rolling.h:252-260) and the local-time range ------
+        {
+            const int n = S.sd.n;
+            const int per = (((n + P.G - 1) / P.G) + 31) & ~31;
+            const int lo = rank * per, hi = min(n, lo + per);
+            const bf_event *ev = P.events + S.sd.ev_off;
+            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN, tmin = INT_MAX, tmax = INT_MIN;
+            for (int i = lo + (int)threadIdx.x; i < hi; i += BF_NT) {
+                const uint2 e = ld_nc_u32x2(ev + i);
+                const int fx = (int)(e.x & 0xffffu), fy = (int)((e.x >> 16) & 0x7fffu), t = (int)e.y;
+                xmin = min(xmin, fx); xmax = max(xmax, fx);
+                ymin = min(ymin, fy); ymax = max(ymax, fy);
+                tmin = min(tmin, t); tmax = max(tmax, t);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+                xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+                ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+                tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+                tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            }
+            if ((threadIdx.x & 31) == 0 && hi > lo) {
+                atomicMin(&S.minmax[0], xmin); atomicMax(&S.minmax[1], xmax);
+                atomicMin(&S.minmax[2], ymin); atomicMax(&S.minmax[3], ymax);
+                atomicMin(&S.minmax[4], tmin); atomicMax(&S.minmax[5], tmax);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && hi > lo) {
+                int *bb = ws->bbox[parity];
+                atomicMin(&bb[0], S.minmax[0]); atomicMax(&bb[1], S.minmax[1]);
+                atomicMin(&bb[2], S.minmax[2]); atomicMax(&bb[3], S.minmax[3]);
+                atomicMin(&bb[4], S.minmax[4]); atomicMax(&bb[5], S.minmax[5]);
+            }
+        }
+        group_barrier(&ws->bar, bar_target, P.G);
+
+        // ---- geometry + guards (optimizer_rolling.h:248-283, 49-58) ---------------------------
+        if (threadIdx.x == 0) {
+            const int *bb = ws->bbox[parity];
+            // the reference starts the minima at RES_X / RES_Y and the maxima at 0 (:252-253)
+            const int x_min = min(P.res_x, __ldcg(&bb[0])), x_max = max(0, __ldcg(&bb[1]));
+            const int y_min = min(P.res_y, __ldcg(&bb[2])), y_max = max(0, __ldcg(&bb[3]));
+            const int t_min = S.sd.n > 0 ? __ldcg(&bb[4]) : 0, t_max = S.sd.n > 0 ? __ldcg(&bb[5]) : 0;
+            bf_make_geom(S.g, x_min, x_max, y_min, y_max, S.sd.scale);
+            bf_make_pack(S.pk, S.sd.n, t_min, t_max);
+            S.slice = 0;
+            if (bf_guard_tiny(S.g, P.res_x, P.res_y)) S.slice = 1;         // :49-55
+            else if (S.sd.n < P.min_events) S.slice = 2;                   // :57-58
+        }
+        __syncthreads();
+        const int guard = S.slice;
+
+        if (guard == 0) {
+            switch (S.sd.scale) {
+                case 1: run_slice<0>(P, S, ws, bar_target, group, rank); break;
+                case 3: run_slice<1>(P, S, ws, bar_target, group, rank); break;
+                default: run_slice<2>(P, S, ws, bar_target, group, rank); break;
+            }
+        } else if (threadIdx.x == 0) {
+            bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
+            S.opt.rc = BF_RC_SKIPPED;
+        }
+        if (guard != 0 && S.sd.has_init && P.want_events) {
+            // set_model already re-projected the events before run() bailed out (dvs_flow.h:218-222)
+            if (threadIdx.x == 0) {
+                const bf_model &m = S.sd.init;
+                bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
+            }
+            __syncthreads();
+            event_pass(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, nullptr, P.nxy);
+        } else if (guard != 0 && P.want_events) {
+            BfProj none;
+            none.dnx = none.dny = none.cx = none.cy = none.div = none.s = 0; none.c = 1;
+            event_pass(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, nullptr, P.nxy);
+        }
+        __syncthreads();
+
+        if (rank == 0 && threadIdx.x == 0) {
+            bf_slice_result r;
+            r.model = S.opt.m;
+            r.rc = S.opt.rc;
+            r.iters = S.opt.iters;
+            r.dividers[0] = S.opt.x_div; r.dividers[1] = S.opt.y_div;
+            r.dividers[2] = S.opt.rot_div; r.dividers[3] = S.opt.div_div;
+            r.x_min = S.g.x_min; r.x_max = S.g.x_max; r.y_min = S.g.y_min; r.y_max = S.g.y_max;
+            r.img_rows = S.g.rows; r.img_cols = S.g.cols;
+            r.x_shift = S.g.x_shift; r.y_shift = S.g.y_shift;
+            r.n_events = S.sd.n;
+            r.flags = (guard == 1 ? BF_FLAG_ALL_NOISE : 0u) | (S.pk.q > 0 ? BF_FLAG_T_QUANTISED : 0u);
+            P.results[slice] = r;
+        }
+        parity ^= 1;
+    }
+}
+
+// ---- stage-level kernels (AccelLib surface; same device functions as the persistent kernel) ----
+
+struct StageParams {
+    int n;
+    const double *pr_x, *pr_y;
+    const int *t;
+    const unsigned char *noise;
+    BfGeom g;
+    BfPack pk;
+    u64 *img;
+    int pitch;
+    double *partials;
+    float *out_img, *out_gx, *out_gy;
+    double *out7;
+};
+
+// AccelLib::get_time_img_cpu's splat loop (accel_lib.h:151-166) as point splats.
+__global__ void bf_stage_splat_kernel(const StageParams P, int clear) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
+        if (P.noise && P.noise[i]) continue;
+        const long long o = event_pixel(P.pr_x[i], P.pr_y[i], P.g, P.pitch);
+        if (o < 0) continue;
+        if (clear) P.img[o] = 0ull;
+        else atomicAdd(P.img + o, bf_pack_value(P.pk, P.t[i]));
+    }
+}
+
+template <int SH>
+__global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StageParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    Acc acc;
+    acc_zero(acc);
+    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, blockIdx.x, gridDim.x, S.p0, S.p1, S.a, P.out_img,
+                         P.out_gx, P.out_gy);
+    acc_block_reduce(acc, S.red, P.partials + blockIdx.x * BF_NSUMS);
+}
+
+__global__ void bf_stage_finish_kernel(const StageParams P, int G) {
+    BfSums s;
+    group_sums(s, P.partials, G);
+    if (threadIdx.x == 0) {
+        bf_model m;
+        bf_sums_to_model(m, s, P.g.rows / 2, P.g.cols / 2);
+        P.out7[0] = m.cx; P.out7[1] = m.cy; P.out7[2] = m.dx; P.out7[3] = m.dy;
+        P.out7[4] = m.rot; P.out7[5] = m.div; P.out7[6] = (double)m.cnt;
+    }
+}
+
+// AccelLib::project_4param_reinit (accel_lib.h:263-267)
+__global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const unsigned short *fr_y,
+                                        const int *t, double *pr_x, double *pr_y, double *nx, double *ny,
+                                        const BfProj q) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double px = pr_x[i], py = pr_y[i], ex, ey;
+        project_event(px, py, ex, ey, (float)fr_x[i], (float)fr_y[i], (float)t[i], q);
+        pr_x[i] = px; pr_y[i] = py;
+        if (nx) nx[i] = ex;
+        if (ny) ny[i] = ey;
+    }
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+
+static thread_local std::string g_err;
+static int g_device = -1;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(BF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct bf_ctx {
+    int device = 0;
+    int sms = 0;
+    int res_x = 0, res_y = 0, max_scale = 3;
+    long long max_events = 0;
+    int max_slices = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // options
+    int opt_group = 0;          // 0 = auto
+    int iter_cap = 20000;
+    int min_events = 1000;
+    long long l2_budget_mb = 64;
+
+    // geometry of the stored images
+    int pitch = 0, rows_alloc = 0;
+    long long img_elems = 0;
+
+    // current launch configuration
+    int G = 0, n_groups = 0;
+
+    // host (pinned)
+    bf_event *h_events = nullptr;
+    SliceDesc *h_slices = nullptr;
+    bf_slice_result *h_results = nullptr;
+    // device
+    bf_event *d_events = nullptr;
+    double2 *d_pr = nullptr;
+    double2 *d_nxy = nullptr;
+    SliceDesc *d_slices = nullptr;
+    bf_slice_result *d_results = nullptr;
+    unsigned char *d_ctrl = nullptr;   // [queue (256 B)][GroupWs x n_groups]
+    size_t ctrl_bytes = 0;
+    double *d_partials = nullptr;
+    u64 *d_images = nullptr;
+    size_t images_bytes = 0;
+    // stage scratch
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // batch state
+    int n_slices = 0;
+    long long n_events = 0;
+    bool uploaded = false, ran = false, have_events = false;
+    long long launches = 0;
+};
+
+static size_t smem_bytes() { return sizeof(Smem); }
+
+static int ensure_device() {
+    if (g_device < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0)
+            return fail(BF_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        g_device = 0;
+    }
+    CU(cudaSetDevice(g_device));
+    return BF_OK;
+}
+
+static int pick_group(bf_ctx *c) {
+    int G = c->opt_group;
+    if (G <= 0) {
+        // as many groups as keep the live images (2 per group) inside the L2 budget
+        const double per_group_mb = 2.0 * (double)c->img_elems * 8.0 / 1048576.0;
+        int groups = (int)std::max(1.0, std::floor((double)c->l2_budget_mb / per_group_mb));
+        groups = std::min(groups, c->sms / 2);
+        if (groups < 1) groups = 1;
+        G = c->sms / groups;
+    }
+    G = std::max(1, std::min(G, c->sms));
+    return G;
+}
+
+static int configure(bf_ctx *c) {
+    const int G = pick_group(c);
+    const int n_groups = std::max(1, c->sms / G);
+    if (G == c->G && n_groups == c->n_groups && c->d_images) return BF_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_images) cudaFree(c->d_images);
+    if (c->d_ctrl) cudaFree(c->d_ctrl);
+    if (c->d_partials) cudaFree(c->d_partials);
+    c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr;
+    c->G = G;
+    c->n_groups = n_groups;
+    c->images_bytes = (size_t)n_groups * 2 * (size_t)c->img_elems * sizeof(u64);
+    CU(cudaMalloc(&c->d_images, c->images_bytes));
+    CU(cudaMemsetAsync(c->d_images, 0, c->images_bytes, c->stream));
+    c->ctrl_bytes = 256 + (size_t)n_groups * sizeof(GroupWs);
+    CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
+    CU(cudaMalloc(&c->d_partials, (size_t)n_groups * G * BF_NSUMS * sizeof(double)));
+    return BF_OK;
+}
+
+extern "C" {
+
+const char *bf_version(void) { return "better_flow_b200 0.1 (sm_100a)"; }
+const char *bf_last_error(void) { return g_err.c_str(); }
+
+int bf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bf_cuda_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(BF_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(BF_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    g_device = device;
+    CU(cudaSetDevice(device));
+    return BF_OK;
+}
+
+bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long max_events, int max_slices) {
+    if (sensor_rows <= 0 || sensor_cols <= 0 || sensor_rows > 32767 || sensor_cols > 32767 ||
+        (max_scale != 1 && max_scale != 3 && max_scale != 5) || max_events <= 0 || max_slices <= 0) {
+        fail(BF_ERR_ARG, "bf_ctx_create: bad arguments (scale must be 1, 3 or 5)");
+        return nullptr;
+    }
+    if (ensure_device() != BF_OK) return nullptr;
+    bf_ctx *c = new bf_ctx();
+    c->device = g_device;
+    c->res_x = sensor_rows; c->res_y = sensor_cols; c->max_scale = max_scale;
+    c->max_events = max_events; c->max_slices = max_slices;
+    cudaDeviceProp prop;
+    auto bail = [&](const char *what, cudaError_t e) -> bf_ctx * {
+        fail(BF_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        bf_ctx_destroy(c);
+        return nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    c->sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { fail(BF_ERR_CUDA, "device lacks cooperative launch"); bf_ctx_destroy(c); return nullptr; }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+
+    const int max_rows = max_scale * sensor_rows, max_cols = max_scale * sensor_cols;
+    c->rows_alloc = ((max_rows + BF_TR - 1) / BF_TR) * BF_TR + 2 * BF_BORDER;
+    c->pitch = ((max_cols + BF_TC - 1) / BF_TC) * BF_TC + 2 * BF_BORDER;
+    c->pitch = (c->pitch + 15) & ~15;   // 128-byte rows
+    c->img_elems = (long long)c->rows_alloc * c->pitch;
+
+    if ((e = cudaMallocHost(&c->h_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMallocHost(events)", e);
+    if ((e = cudaMallocHost(&c->h_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMallocHost(slices)", e);
+    if ((e = cudaMallocHost(&c->h_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMallocHost(results)", e);
+    if ((e = cudaMalloc(&c->d_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMalloc(events)", e);
+    if ((e = cudaMalloc(&c->d_pr, (size_t)max_events * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc(pr)", e);
+    if ((e = cudaMalloc(&c->d_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMalloc(slices)", e);
+    if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
+
+    if ((e = cudaFuncSetAttribute(bf_minimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    return c;
+}
+
+void bf_ctx_destroy(bf_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
+    cudaFree(c->d_events); cudaFree(c->d_pr); cudaFree(c->d_nxy); cudaFree(c->d_slices);
+    cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images);
+    cudaFree(c->d_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
+    if (!c || !key) return fail(BF_ERR_ARG, "null argument");
+    if (!strcmp(key, "group_size")) c->opt_group = (int)value;
+    else if (!strcmp(key, "iter_cap")) c->iter_cap = (int)std::max(1LL, value);
+    else if (!strcmp(key, "min_events")) c->min_events = (int)value;
+    else if (!strcmp(key, "l2_budget_mb")) c->l2_budget_mb = std::max(1LL, value);
+    else return fail(BF_ERR_ARG, "unknown option '%s'", key);
+    return BF_OK;
+}
+
+long long bf_ctx_get_option(bf_ctx *c, const char *key) {
+    if (!c || !key) return -1;
+    if (!strcmp(key, "group_size")) return c->G ? c->G : pick_group(c);
+    if (!strcmp(key, "n_groups")) return c->n_groups ? c->n_groups : std::max(1, c->sms / pick_group(c));
+    if (!strcmp(key, "iter_cap")) return c->iter_cap;
+    if (!strcmp(key, "min_events")) return c->min_events;
+    if (!strcmp(key, "l2_budget_mb")) return c->l2_budget_mb;
+    if (!strcmp(key, "sms")) return c->sms;
+    if (!strcmp(key, "image_bytes")) return c->img_elems * 8;
+    if (!strcmp(key, "smem_bytes")) return (long long)smem_bytes();
+    return -1;
+}
+
+long long bf_ctx_launch_count(bf_ctx *c) { return c ? c->launches : 0; }
+
+int bf_batch_reset(bf_ctx *c) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    c->n_slices = 0; c->n_events = 0;
+    c->uploaded = c->ran = c->have_events = false;
+    return BF_OK;
+}
+
+static int add_desc(bf_ctx *c, long long off, int n, int scale, int max_iter, const bf_model *init) {
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported (1, 3 or 5)", scale);
+    if (scale > c->max_scale) return fail(BF_ERR_ARG, "scale %d exceeds the context's max_scale %d", scale, c->max_scale);
+    if (c->n_slices >= c->max_slices) return fail(BF_ERR_ARG, "batch full (%d slices)", c->max_slices);
+    SliceDesc &d = c->h_slices[c->n_slices];
+    memset(&d, 0, sizeof d);
+    d.ev_off = off; d.n = n; d.scale = scale; d.max_iter = max_iter;
+    d.has_init = init ? 1 : 0;
+    if (init) d.init = *init;
+    c->uploaded = c->ran = false;
+    return c->n_slices++;
+}
+
+static int check_coords(bf_ctx *c, unsigned fx, unsigned fy) {
+    if (fx >= (unsigned)c->res_x || fy >= (unsigned)c->res_y)
+        return fail(BF_ERR_ARG, "event (%u,%u) outside the %dx%d sensor", fx, fy, c->res_x, c->res_y);
+    return BF_OK;
+}
+
+int bf_batch_add(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,
+                 const uint8_t *noise, int n, int scale, int max_iter, const bf_model *init) {
+    if (!c || n < 0 || (n > 0 && (!fr_x || !fr_y || !t_ns))) return fail(BF_ERR_ARG, "bf_batch_add: bad arguments");
+    if (c->n_events + n > c->max_events) return fail(BF_ERR_ARG, "batch event capacity exceeded (%lld)", c->max_events);
+    bf_event *dst = c->h_events + c->n_events;
+    unsigned bad = 0;
+    for (int i = 0; i < n; ++i) {
+        bad |= (unsigned)(fr_x[i] >= c->res_x) | (unsigned)(fr_y[i] >= c->res_y);
+        dst[i].fr_x = fr_x[i];
+        dst[i].fr_y = (uint16_t)(fr_y[i] | ((noise && noise[i]) ? BF_EVENT_NOISE : 0u));
+        dst[i].t_ns = t_ns[i];
+    }
+    if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
+    const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
+    if (slot >= 0) c->n_events += n;
+    return slot;
+}
+
+int bf_batch_add_packed(bf_ctx *c, const bf_event *events, int n, int scale, int max_iter, const bf_model *init) {
+    if (!c || n < 0 || (n > 0 && !events)) return fail(BF_ERR_ARG, "bf_batch_add_packed: bad arguments");
+    if (c->n_events + n > c->max_events) return fail(BF_ERR_ARG, "batch event capacity exceeded (%lld)", c->max_events);
+    memcpy(c->h_events + c->n_events, events, (size_t)n * sizeof(bf_event));
+    const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
+    if (slot >= 0) c->n_events += n;
+    return slot;
+}
+
+bf_event *bf_batch_staging(bf_ctx *c, long long *capacity) {
+    if (!c) return nullptr;
+    if (capacity) *capacity = c->max_events;
+    return c->h_events;
+}
+
+int bf_batch_add_staged(bf_ctx *c, long long offset, int n, int scale, int max_iter, const bf_model *init) {
+    if (!c || n < 0 || offset < 0 || offset + n > c->max_events) return fail(BF_ERR_ARG, "bf_batch_add_staged: bad range");
+    const int slot = add_desc(c, offset, n, scale, max_iter, init);
+    if (slot >= 0) c->n_events = std::max(c->n_events, offset + n);
+    return slot;
+}
+
+int bf_batch_upload(bf_ctx *c) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (c->n_events > 0)
+        CU(cudaMemcpyAsync(c->d_events, c->h_events, (size_t)c->n_events * sizeof(bf_event), cudaMemcpyHostToDevice, c->stream));
+    if (c->n_slices > 0)
+        CU(cudaMemcpyAsync(c->d_slices, c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->stream));
+    c->uploaded = true;
+    return BF_OK;
+}
+
+int bf_batch_launch(bf_ctx *c, int want_events) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    if (!c->uploaded) return fail(BF_ERR_STATE, "bf_batch_launch before bf_batch_upload");
+    CU(cudaSetDevice(c->device));
+    if (c->n_slices == 0) { c->ran = true; return BF_OK; }
+    int rc = configure(c);
+    if (rc != BF_OK) return rc;
+    if (want_events && !c->d_nxy) CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
+    CU(cudaMemsetAsync(c->d_ctrl, 0, c->ctrl_bytes, c->stream));
+    KParams P;
+    P.events = c->d_events; P.pr = c->d_pr; P.nxy = want_events ? c->d_nxy : nullptr;
+    P.slices = c->d_slices; P.results = c->d_results; P.n_slices = c->n_slices;
+    P.queue = reinterpret_cast<int *>(c->d_ctrl);
+    P.ws = reinterpret_cast<GroupWs *>(c->d_ctrl + 256);
+    P.partials = c->d_partials; P.images = c->d_images; P.img_elems = c->img_elems; P.pitch = c->pitch;
+    P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
+    P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
+    void *args[] = {&P};
+    CU(cudaLaunchCooperativeKernel((void *)bf_minimize_kernel, dim3(c->n_groups * c->G), dim3(BF_NT), args,
+                                   smem_bytes(), c->stream));
+    c->launches += 1;
+    c->ran = true;
+    c->have_events = want_events != 0;
+    return BF_OK;
+}
+
+int bf_batch_download(bf_ctx *c) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    if (!c->ran) return fail(BF_ERR_STATE, "bf_batch_download before bf_batch_launch");
+    if (c->n_slices > 0)
+        CU(cudaMemcpyAsync(c->h_results, c->d_results, (size_t)c->n_slices * sizeof(bf_slice_result), cudaMemcpyDeviceToHost, c->stream));
+    return BF_OK;
+}
+
+int bf_batch_sync(bf_ctx *c) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_batch_run(bf_ctx *c, int want_events) {
+    int rc;
+    if ((rc = bf_batch_upload(c)) != BF_OK) return rc;
+    if ((rc = bf_batch_launch(c, want_events)) != BF_OK) return rc;
+    if ((rc = bf_batch_download(c)) != BF_OK) return rc;
+    return bf_batch_sync(c);
+}
+
+int bf_batch_time_launches(bf_ctx *c, int reps, int want_events, float *ms) {
+    if (!c || reps <= 0 || !ms) return fail(BF_ERR_ARG, "bf_batch_time_launches: bad arguments");
+    int rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    for (int r = 0; r < reps; ++r)
+        if ((rc = bf_batch_launch(c, want_events)) != BF_OK) return rc;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return BF_OK;
+}
+
+int bf_batch_size(bf_ctx *c) { return c ? c->n_slices : 0; }
+
+int bf_batch_result(bf_ctx *c, int slot, bf_slice_result *out) {
+    if (!c || !out || slot < 0 || slot >= c->n_slices) return fail(BF_ERR_ARG, "bf_batch_result: bad slot");
+    if (!c->ran) return fail(BF_ERR_STATE, "bf_batch_result before the batch ran");
+    *out = c->h_results[slot];
+    return BF_OK;
+}
+
+int bf_batch_events(bf_ctx *c, int slot, double *pr_x, double *pr_y, double *nx, double *ny) {
+    if (!c || slot < 0 || slot >= c->n_slices) return fail(BF_ERR_ARG, "bf_batch_events: bad slot");
+    if (!c->ran || !c->have_events) return fail(BF_ERR_STATE, "bf_batch_events needs a launch with want_events");
+    const SliceDesc &d = c->h_slices[slot];
+    if (d.n == 0) return BF_OK;
+    std::vector<double2> tmp((size_t)d.n);
+    CU(cudaStreamSynchronize(c->stream));
+    if (pr_x || pr_y) {
+        CU(cudaMemcpy(tmp.data(), c->d_pr + d.ev_off, (size_t)d.n * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d.n; ++i) { if (pr_x) pr_x[i] = tmp[i].x; if (pr_y) pr_y[i] = tmp[i].y; }
+    }
+    if (nx || ny) {
+        CU(cudaMemcpy(tmp.data(), c->d_nxy + d.ev_off, (size_t)d.n * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d.n; ++i) { if (nx) nx[i] = tmp[i].x; if (ny) ny[i] = tmp[i].y; }
+    }
+    return BF_OK;
+}
+
+int bf_minimize(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, const uint8_t *noise,
+                int n, int scale, int max_iter, const bf_model *init, bf_slice_result *out, double *pr_x,
+                double *pr_y, double *nx, double *ny) {
+    int rc;
+    if ((rc = bf_batch_reset(c)) != BF_OK) return rc;
+    if ((rc = bf_batch_add(c, fr_x, fr_y, t_ns, noise, n, scale, max_iter, init)) < 0) return rc;
+    const int want = (pr_x || pr_y || nx || ny) ? 1 : 0;
+    if ((rc = bf_batch_run(c, want)) != BF_OK) return rc;
+    bf_slice_result r;
+    if ((rc = bf_batch_result(c, 0, &r)) != BF_OK) return rc;
+    if (out) *out = r;
+    if (want && (rc = bf_batch_events(c, 0, pr_x, pr_y, nx, ny)) != BF_OK) return rc;
+    return r.rc;
+}
+
+// ---- stage-level entry points -----------------------------------------------------------------
+
+static int stage_alloc(bf_ctx *c, size_t bytes) {
+    if (bytes <= c->stage_bytes) return BF_OK;
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr; c->stage_bytes = 0;
+    CU(cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return BF_OK;
+}
+
+static int stage_image(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns,
+                       const uint8_t *noise, int w, int h, int scale, int x_sh, int y_sh, float *out_img,
+                       double *out7, float *out_gx, float *out_gy) {
+    if (!c || n < 0 || (n > 0 && (!pr_x || !pr_y || !t_ns))) return fail(BF_ERR_ARG, "stage: bad arguments");
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported", scale);
+    const int rows = w + scale, cols = h + scale;
+    if (w < 0 || h < 0 || rows > c->rows_alloc - 2 * BF_BORDER || cols > c->pitch - 2 * BF_BORDER)
+        return fail(BF_ERR_ARG, "image %dx%d exceeds the context's capacity", rows, cols);
+    CU(cudaSetDevice(c->device));
+    int rc = configure(c);
+    if (rc != BF_OK) return rc;
+    const size_t P = (size_t)rows * cols;
+    const int grid = c->sms;
+    // scratch layout: pr_x, pr_y (f64) | t (i32) | noise (u8) | partials | out7 | img | gx | gy
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_px = take((size_t)n * 8), o_py = take((size_t)n * 8), o_t = take((size_t)n * 4), o_nz = take((size_t)n);
+    const size_t o_part = take((size_t)grid * BF_NSUMS * 8), o_out7 = take(64);
+    const size_t o_img = take(P * 4), o_gx = take(P * 4), o_gy = take(P * 4);
+    if ((rc = stage_alloc(c, off)) != BF_OK) return rc;
+    unsigned char *base = (unsigned char *)c->d_stage;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(base + o_px, pr_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(base + o_py, pr_y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(base + o_t, t_ns, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (noise) CU(cudaMemcpyAsync(base + o_nz, noise, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    StageParams S;
+    S.n = n;
+    S.pr_x = (const double *)(base + o_px); S.pr_y = (const double *)(base + o_py);
+    S.t = (const int *)(base + o_t); S.noise = noise ? (base + o_nz) : nullptr;
+    memset(&S.g, 0, sizeof S.g);
+    S.g.w = w; S.g.h = h; S.g.rows = rows; S.g.cols = cols; S.g.scale = scale; S.g.half = scale / 2;
+    S.g.x_sh = x_sh; S.g.y_sh = y_sh; S.g.x_shift = x_sh; S.g.y_shift = y_sh;
+    int32_t t_min = 0, t_max = 0;
+    if (n > 0) { t_min = *std::min_element(t_ns, t_ns + n); t_max = *std::max_element(t_ns, t_ns + n); }
+    bf_make_pack(S.pk, n, t_min, t_max);
+    S.img = c->d_images; S.pitch = c->pitch;
+    S.partials = (double *)(base + o_part);
+    S.out_img = (float *)(base + o_img); S.out_gx = (float *)(base + o_gx); S.out_gy = (float *)(base + o_gy);
+    S.out7 = (double *)(base + o_out7);
+    const int sb = std::max(1, std::min(4 * c->sms, (n + 255) / 256));
+    if (n > 0) { bf_stage_splat_kernel<<<sb, 256, 0, c->stream>>>(S, 0); c->launches++; }
+    switch (scale) {
+        case 1: bf_stage_image_kernel<0><<<grid, BF_NT, smem_bytes(), c->stream>>>(S); break;
+        case 3: bf_stage_image_kernel<1><<<grid, BF_NT, smem_bytes(), c->stream>>>(S); break;
+        default: bf_stage_image_kernel<2><<<grid, BF_NT, smem_bytes(), c->stream>>>(S); break;
+    }
+    bf_stage_finish_kernel<<<1, 32, 0, c->stream>>>(S, grid);
+    c->launches += 2;
+    if (n > 0) { bf_stage_splat_kernel<<<sb, 256, 0, c->stream>>>(S, 1); c->launches++; }   // restore the all-zero image
+    CU(cudaGetLastError());
+    if (out_img) CU(cudaMemcpyAsync(out_img, S.out_img, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_gx) CU(cudaMemcpyAsync(out_gx, S.out_gx, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_gy) CU(cudaMemcpyAsync(out_gy, S.out_gy, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out7) CU(cudaMemcpyAsync(out7, S.out7, 7 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns, const uint8_t *noise,
+                int w, int h, int scale, int x_sh, int y_sh, float *out) {
+    if (!out) return fail(BF_ERR_ARG, "bf_time_img: null output");
+    return stage_image(c, n, pr_x, pr_y, t_ns, noise, w, h, scale, x_sh, y_sh, out, nullptr, nullptr, nullptr);
+}
+
+int bf_fast_model(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns, const uint8_t *noise,
+                  int w, int h, int scale, int x_sh, int y_sh, double *out7, float *gx, float *gy) {
+    if (!out7) return fail(BF_ERR_ARG, "bf_fast_model: null output");
+    return stage_image(c, n, pr_x, pr_y, t_ns, noise, w, h, scale, x_sh, y_sh, nullptr, out7, gx, gy);
+}
+
+int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, double *pr_x,
+               double *pr_y, double *nx, double *ny, double dnx, double dny, double cx, double cy, double div,
+               double crl) {
+    if (!c || n < 0 || (n > 0 && (!fr_x || !fr_y || !t_ns || !pr_x || !pr_y))) return fail(BF_ERR_ARG, "bf_project: bad arguments");
+    if (n == 0) return BF_OK;
+    CU(cudaSetDevice(c->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_fx = take((size_t)n * 2), o_fy = take((size_t)n * 2), o_t = take((size_t)n * 4);
+    const size_t o_px = take((size_t)n * 8), o_py = take((size_t)n * 8), o_nx = take((size_t)n * 8), o_ny = take((size_t)n * 8);
+    int rc;
+    if ((rc = stage_alloc(c, off)) != BF_OK) return rc;
+    unsigned char *base = (unsigned char *)c->d_stage;
+    CU(cudaMemcpyAsync(base + o_fx, fr_x, (size_t)n * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(base + o_fy, fr_y, (size_t)n * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(base + o_t, t_ns, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(base + o_px, pr_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(base + o_py, pr_y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    BfProj q;
+    bf_make_proj(q, dnx, dny, cx, cy, div, crl);   // cos/sin on the host (glibc), as the reference
+    const int sb = std::max(1, std::min(4 * c->sms, (n + 255) / 256));
+    bf_stage_project_kernel<<<sb, 256, 0, c->stream>>>(n, (const unsigned short *)(base + o_fx),
+                                                        (const unsigned short *)(base + o_fy), (const int *)(base + o_t),
+                                                        (double *)(base + o_px), (double *)(base + o_py),
+                                                        (double *)(base + o_nx), (double *)(base + o_ny), q);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pr_x, base + o_px, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(pr_y, base + o_py, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (nx) CU(cudaMemcpyAsync(nx, base + o_nx, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (ny) CU(cudaMemcpyAsync(ny, base + o_ny, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+/* bf_cuda.h -- C ABI of the B200-native motion-compensation backend.
+ *
+ * This is the drop-in boundary for better-flow's per-time-slice hot path.  In the reference the
+ * accelerator seam is class AccelLib (better_flow_core/include/better_flow/accel_lib.h:14-616),
+ * owned by value by OptimizerRolling (optimizer_rolling.h:19) and selected at run time by
+ * OpenCLDriver::enabled (accel_lib.h:41,46; bf_motion_compensator.cpp:132-133).  Every entry
+ * point below names the reference interface it replaces.  All paths in comments are relative
+ * to /root/reference/better_flow_core/.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host array; the library
+ * owns all device memory behind the opaque bf_ctx; one CUDA stream per context; a context is
+ * not thread-safe, distinct contexts are.  Return values: >= 0 success (see each function),
+ * < 0 error (bf_last_error() gives the text).  There is NO CPU fallback: without a CUDA device
+ * every compute entry point fails with BF_ERR_CUDA.
+ *
+ * Axis convention is the reference's: fr_x = sensor ROW (file "y"), fr_y = sensor COLUMN
+ * (file "x") (bf_motion_compensator.cpp:200); image row index = "x" (accel_lib.h:148).
+ */
+#ifndef BF_CUDA_H
+#define BF_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_OK 0
+#define BF_ERR_ARG (-1)      /* bad argument / capacity exceeded */
+#define BF_ERR_CUDA (-2)     /* CUDA runtime error or no device */
+#define BF_ERR_STATE (-3)    /* call out of sequence */
+
+/* run() outcomes stored in bf_slice_result.rc */
+#define BF_RC_OK 0           /* optimised                      (optimizer_rolling.h:124) */
+#define BF_RC_SKIPPED 1      /* guard hit: tiny window or < 1000 events (optimizer_rolling.h:49-58) */
+#define BF_RC_ITER_CAP 2     /* safety cap on iterations reached (the reference has none) */
+#define BF_RC_DEGENERATE 3   /* no pixel above the 1e-6 occupancy threshold: the reference divides
+                                0/0 (object_model.cpp:122-125) and never terminates; we stop */
+
+/* result flags */
+#define BF_FLAG_ALL_NOISE 1u /* tiny-window guard fired: the reference marks every event of the
+                                slice as noise (optimizer_rolling.h:52-53) */
+#define BF_FLAG_T_QUANTISED 2u /* slice too long/dense for exact 64-bit packed sums; timestamps were
+                                  right-shifted (never at BASELINE sizes) */
+
+/* High bit of bf_event.fr_y marks an event whose `noise` flag is already set (event.h:11):
+ * it is warped but not splatted (accel_lib.h:152). */
+#define BF_EVENT_NOISE 0x8000u
+
+/* Compact event record, 8 bytes.  Replaces the 152-byte AoS `Event` (event.h:7-34) on the device:
+ * fr_x, fr_y as the reference stores them, t_ns = Event::t after set_local_time (event.h:61-63),
+ * i.e. timestamp - slice_start as a signed offset in ns. */
+typedef struct bf_event {
+    uint16_t fr_x;
+    uint16_t fr_y;
+    int32_t t_ns;
+} bf_event;
+
+/* POD image of ObjectModel's state (object_model.h:10-13), same order. */
+typedef struct bf_model {
+    double cx, cy, dx, dy, rot, div;
+    uint32_t cnt;
+    uint32_t pad_;
+    double total_dx, total_dy, total_rot, total_div;
+} bf_model;
+
+/* Everything OptimizerRolling exposes after run() for one slice. */
+typedef struct bf_slice_result {
+    bf_model model;          /* get_model()                       (optimizer_rolling.h:285-287) */
+    int32_t rc;              /* run() return value + BF_RC_* extensions */
+    int32_t iters;           /* run()'s local itercount           (optimizer_rolling.h:60) */
+    float dividers[4];       /* x, y, rot, div dividers           (optimizer_rolling.h:36) */
+    int32_t x_min, x_max, y_min, y_max;   /* bbox                 (optimizer_rolling.h:252-260) */
+    int32_t img_rows, img_cols;           /* scale_img_x/y        (optimizer_rolling.h:276-277) */
+    double x_shift, y_shift;              /*                      (optimizer_rolling.h:279-282) */
+    int32_t n_events;
+    uint32_t flags;          /* BF_FLAG_* */
+} bf_slice_result;
+
+typedef struct bf_ctx bf_ctx;
+
+/* ---- device / context --------------------------------------------------------------------- */
+
+/* Replaces OpenCLDriver::init() (src/opencl_driver.cpp:14-60): selects the CUDA device.
+ * Returns BF_OK or BF_ERR_CUDA. */
+int bf_cuda_init(int device);
+int bf_device_count(void);
+const char *bf_last_error(void);
+const char *bf_version(void);
+
+/* Replaces AccelLib::init_gpu (accel_lib.h:71-145), but pooled: the reference re-allocates device
+ * buffers for every slice (a fresh OptimizerRolling per slice, dvs_flow.h:210); a context is
+ * created once and reused.
+ *   sensor_rows/cols   RES_X / RES_Y (common.h:39-40), now run-time
+ *   max_scale          largest `scale` that will be used (1, 3 or 5)
+ *   max_events         total event capacity of one batch
+ *   max_slices         slice capacity of one batch */
+bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long max_events, int max_slices);
+void bf_ctx_destroy(bf_ctx *ctx);
+
+/* Tunables.  Keys: "group_size" (CTAs cooperating on one slice; 0 = auto), "iter_cap",
+ * "min_events" (the reference's 1000, optimizer_rolling.h:57). */
+int bf_ctx_set_option(bf_ctx *ctx, const char *key, long long value);
+long long bf_ctx_get_option(bf_ctx *ctx, const char *key);
+
+/* ---- batched minimisation: N independent slices in one persistent launch -------------------
+ * A "slice" is what DVS_flow::recompute hands to OptimizerRolling (dvs_flow.h:196-222):
+ * events in iteration order, local times, scale, max_iter and an optional warm-start model. */
+
+int bf_batch_reset(bf_ctx *ctx);
+
+/* set_cloud + set_time + set_maxiter + [set_model] (optimizer_rolling.h:236-299).
+ *   noise      nullable per-event flags
+ *   init       nullable; NULL == --stm-disable (dvs_flow.h:218-219)
+ * Returns the slot index (>= 0) of the slice inside the batch. */
+int bf_batch_add(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,
+                 const uint8_t *noise, int n, int scale, int max_iter, const bf_model *init);
+/* Same, events already in the compact 8-byte layout (no host-side packing pass). */
+int bf_batch_add_packed(bf_ctx *ctx, const bf_event *events, int n, int scale, int max_iter,
+                        const bf_model *init);
+
+/* Pinned host staging area the batch is assembled in (so callers can fill it in place):
+ * returns the base of the event staging buffer; *capacity = max_events. */
+bf_event *bf_batch_staging(bf_ctx *ctx, long long *capacity);
+/* Declare a slice that already lives in the staging buffer at [offset, offset+n). */
+int bf_batch_add_staged(bf_ctx *ctx, long long offset, int n, int scale, int max_iter,
+                        const bf_model *init);
+
+/* Asynchronous pieces (all on the context's stream) ... */
+int bf_batch_upload(bf_ctx *ctx);                    /* H2D of events + slice table */
+int bf_batch_launch(bf_ctx *ctx, int want_events);   /* OptimizerRolling::run() for every slice */
+int bf_batch_download(bf_ctx *ctx);                  /* D2H of the result records */
+int bf_batch_sync(bf_ctx *ctx);
+/* ... and the synchronous composition upload -> launch -> download -> sync. */
+int bf_batch_run(bf_ctx *ctx, int want_events);
+
+/* Times `reps` back-to-back launches on the resident batch with CUDA events on the context's
+ * stream (inputs already in HBM).  Returns total milliseconds in *ms. */
+int bf_batch_time_launches(bf_ctx *ctx, int reps, int want_events, float *ms);
+/* Number of kernels launched by this context so far. */
+long long bf_ctx_launch_count(bf_ctx *ctx);
+
+int bf_batch_size(bf_ctx *ctx);
+int bf_batch_result(bf_ctx *ctx, int slot, bf_slice_result *out);
+/* Replaces AccelLib::writeout_events (accel_lib.h:310-329): per-event state after run().
+ * Needs want_events != 0 at launch.  Any pointer may be NULL. */
+int bf_batch_events(bf_ctx *ctx, int slot, double *pr_x, double *pr_y, double *nx, double *ny);
+
+/* One slice, synchronously == one OptimizerRolling::run() (optimizer_rolling.h:48-125).
+ * Returns the run() code (BF_RC_*) or < 0. */
+int bf_minimize(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,
+                const uint8_t *noise, int n, int scale, int max_iter, const bf_model *init,
+                bf_slice_result *out, double *pr_x, double *pr_y, double *nx, double *ny);
+
+/* ---- stage-level entry points (the AccelLib surface; used by the kernel parity tests) ------ */
+
+/* AccelLib::get_time_img (accel_lib.h:211-217 -> 147-178): mean-timestamp image in seconds,
+ * (w+scale) x (h+scale) floats, row-major. */
+int bf_time_img(bf_ctx *ctx, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns,
+                const uint8_t *noise, int w, int h, int scale, int x_sh, int y_sh, float *out);
+
+/* AccelLib::fast_model(get_time_img(...)) (accel_lib.h:337-341 -> object_model.h:31-34):
+ * out7 = cx, cy (image units), dx, dy, rot, div, cnt.  gx/gy nullable: the Scharr images of
+ * AccelLib::Sobel (accel_lib.h:400-434, 513-543). */
+int bf_fast_model(bf_ctx *ctx, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns,
+                  const uint8_t *noise, int w, int h, int scale, int x_sh, int y_sh,
+                  double *out7, float *gx, float *gy);
+
+/* AccelLib::project_4param_reinit (accel_lib.h:263-267 -> event.h:99-110,164-168), in place on
+ * pr_x/pr_y; nx/ny nullable outputs. */
+int bf_project(bf_ctx *ctx, int n, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,
+               double *pr_x, double *pr_y, double *nx, double *ny,
+               double dnx, double dny, double cx, double cy, double div, double crl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BF_CUDA_H */

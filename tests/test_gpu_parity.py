@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/bf_cuda.h), against the oracle.
+
+Two oracles modes (oracle/bf_oracle.c): accum_mode=0 is the reference's arithmetic bit for bit
+(pinned against the compiled reference and the golden vectors in test_oracle.py); accum_mode=1
+differs only in accumulating the time image with exact integer sums, which is what the CUDA path
+does -- so against mode 1 the CUDA path must agree to the last bit (integer / byte / index work)
+or to ~1e-12 (the fp64 reductions, which associate differently), and against mode 0 within the
+contract's 1e-4 relative on (total_dx, total_dy)."""
+import numpy as np
+import pytest
+
+from better_flow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_CONTRACT = 1e-4     # BASELINE.json north_star: per-slice (dx,dy) within 1e-4 relative
+REL_EXACT = 1e-9        # vs the exact-sum oracle (only fp64 re-association differs)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def slices_240(seed, slice_s, n=3, rate=3e6, **kw):
+    st = synth.make_stream(240, 180, rate, slice_s * n, seed=seed, **kw)
+    return synth.cut_slices(st, slice_s)[:n]
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_project_bit_exact(ctx240, oracle_port, seed):
+    rng = np.random.default_rng(seed)
+    sl = slices_240(seed, 0.01, 1)[0]
+    n = len(sl.fr_x)
+    pr_x = sl.fr_x + rng.normal(0, 2.0, n)
+    pr_y = sl.fr_y + rng.normal(0, 2.0, n)
+    args = (-0.043, 0.081, 91.3, 118.7, 3.1e-5, -2.2e-4)
+    got = ctx240.project(sl.fr_x, sl.fr_y, sl.t_ns, pr_x, pr_y, *args)
+    want = oracle_port.project(sl.fr_x, sl.fr_y, sl.t_ns, pr_x, pr_y, *args)
+    for g, w, name in zip(got, want, ("pr_x", "pr_y", "nx", "ny")):
+        assert np.array_equal(g, w), name
+
+
+@pytest.mark.parametrize("scale", [1, 3, 5])
+def test_time_img_and_model(ctx240, oracle_port, scale):
+    sl = slices_240(3, 0.01, 1)[0]
+    su = oracle_port.setup_slice(sl.fr_x, sl.fr_y, 180, 240, scale)
+    rng = np.random.default_rng(5)
+    n = len(sl.fr_x)
+    pr_x = sl.fr_x + rng.normal(0, 1.5, n)   # some events leave the window -> rejection path
+    pr_y = sl.fr_y + rng.normal(0, 1.5, n)
+    noise = (rng.uniform(size=n) < 0.02).astype(np.uint8)
+    a = (pr_x, pr_y, sl.t_ns, su.wsize_x, su.wsize_y, scale, int(su.x_shift), int(su.y_shift))
+    img = ctx240.time_img(*a, noise=noise)
+    exact = oracle_port.time_img(*a, noise=noise, accum_mode=1)
+    ref = oracle_port.time_img(*a, noise=noise, accum_mode=0)
+    assert img.shape == exact.shape
+    assert np.array_equal(img, exact), "time image differs from the exact-sum oracle"
+    assert np.max(np.abs(img - ref)) < 1e-6, "time image vs reference accumulation"
+    out7, gx, gy = ctx240.fast_model(*a, noise=noise, want_grad=True)
+    w7, wgx, wgy = oracle_port.model(exact, want_grad=True)
+    assert np.array_equal(gx, wgx) and np.array_equal(gy, wgy), "Scharr images must be bit exact"
+    assert out7[6] == w7[6], "occupied pixel count"
+    assert out7[0] == w7[0] and out7[1] == w7[1], "centre of mass (exact integer sums)"
+    assert np.all(rel(out7[2:6], w7[2:6]) < 1e-10), rel(out7[2:6], w7[2:6])
+
+
+@pytest.mark.parametrize("slice_s,max_iter,scale", [(0.010, 10, 3), (0.010, -1, 3), (0.030, -1, 3), (0.010, 25, 1)])
+def test_minimize_parity(ctx240, oracle_port, slice_s, max_iter, scale):
+    for sl in slices_240(11, slice_s, 2):
+        got = ctx240.minimize(sl.fr_x, sl.fr_y, sl.t_ns, scale=scale, max_iter=max_iter, want_events=True)
+        exact = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, scale=scale, max_iter=max_iter, accum_mode=1, want_events=True)
+        ref = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, scale=scale, max_iter=max_iter, accum_mode=0)
+        assert got["rc"] == exact["rc"] == 0
+        for k in ("x_min", "x_max", "y_min", "y_max", "img_rows", "img_cols", "x_shift", "y_shift"):
+            assert got[k] == exact[k], k
+        assert got["iters"] == exact["iters"]
+        assert np.array_equal(got["dividers"], exact["dividers"])
+        assert got["model"][6] == exact["model"][6]
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < REL_EXACT), rel(got["model"], exact["model"])
+        assert np.max(np.abs(got["pr_x"] - exact["pr_x"])) < 1e-9
+        assert np.max(np.abs(got["nx"] - exact["nx"])) < 1e-9
+        # the contract: within 1e-4 relative of the reference CPU path
+        assert np.all(rel(got["model"][7:9], ref["model"][7:9]) < REL_CONTRACT)
+
+
+def test_rotating_expanding_stream(ctx240, oracle_port):
+    st = synth.make_stream(240, 180, 3e6, 0.02, seed=21, vel=(-150.0, 60.0), omega=1.5, expand=0.8)
+    for sl in synth.cut_slices(st, 0.01)[:2]:
+        got = ctx240.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=40)
+        exact = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=40, accum_mode=1)
+        ref = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=40, accum_mode=0)
+        assert got["iters"] == exact["iters"]
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < 1e-8)
+        assert np.all(rel(got["model"][7:9], ref["model"][7:9]) < REL_CONTRACT)
+
+
+def test_warm_start(ctx240, oracle_port):
+    a, b = slices_240(31, 0.01, 2)
+    first = oracle_port.minimize(a.fr_x, a.fr_y, a.t_ns, max_iter=10, accum_mode=1)
+    got = ctx240.minimize(b.fr_x, b.fr_y, b.t_ns, max_iter=10, init=first["model"], want_events=True)
+    exact = oracle_port.minimize(b.fr_x, b.fr_y, b.t_ns, max_iter=10, init_model=first["model"], accum_mode=1, want_events=True)
+    assert got["iters"] == exact["iters"]
+    assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < REL_EXACT)
+    assert np.max(np.abs(got["pr_y"] - exact["pr_y"])) < 1e-9
+
+
+def test_batch_equals_single_and_is_deterministic(ctx240):
+    sls = slices_240(41, 0.01, 6)
+    singles = [ctx240.minimize(s.fr_x, s.fr_y, s.t_ns, max_iter=10) for s in sls]
+    for _ in range(2):
+        ctx240.reset()
+        for s in sls:
+            ctx240.add(s.fr_x, s.fr_y, s.t_ns, 3, 10)
+        ctx240.run()
+        for one, res in zip(singles, ctx240.results()):
+            assert res["iters"] == one["iters"]
+            assert np.array_equal(res["model"], one["model"]), "batched result must be bit-identical"
+
+
+def test_guards_and_edge_cases(ctx240, oracle_port):
+    sl = slices_240(51, 0.01, 1)[0]
+    # fewer than 1000 events -> run() returns 1 (optimizer_rolling.h:57-58)
+    r = ctx240.minimize(sl.fr_x[:999], sl.fr_y[:999], sl.t_ns[:999], want_events=True)
+    assert r["rc"] == 1 and r["iters"] == 0
+    assert np.array_equal(r["pr_x"], sl.fr_x[:999].astype(np.float64))
+    # tiny window -> all events become noise, run() returns 1 (optimizer_rolling.h:49-55)
+    m = (sl.fr_x < 8) & (sl.fr_y < 8)
+    fx = np.tile(sl.fr_x[m], 40)[:1500]
+    fy = np.tile(sl.fr_y[m], 40)[:1500]
+    tt = np.resize(sl.t_ns, 1500)
+    r = ctx240.minimize(fx, fy, tt)
+    w = oracle_port.minimize(fx, fy, tt)
+    assert r["rc"] == w["rc"] == 1 and (r["flags"] & 1) and np.all(w["noise"] == 1)
+    # empty slice
+    z = np.zeros(0, dtype=np.uint16)
+    r = ctx240.minimize(z, z, np.zeros(0, dtype=np.int32))
+    assert r["rc"] == 1 and r["n_events"] == 0
+    # pre-marked noise events are warped but not splatted (accel_lib.h:152)
+    noise = (np.arange(len(sl.fr_x)) % 7 == 0).astype(np.uint8)
+    g = ctx240.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=5, noise=noise)
+    e = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=5, noise=noise, accum_mode=1)
+    assert g["iters"] == e["iters"] and g["model"][6] == e["model"][6]
+    assert np.all(rel(g["model"][7:11], e["model"][7:11]) < REL_EXACT)
+    # negative local times (events older than the slice start, event.h:61-63)
+    g = ctx240.minimize(sl.fr_x, sl.fr_y, sl.t_ns - 3_000_000, max_iter=5)
+    e = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns.astype(np.int64) - 3_000_000, max_iter=5, accum_mode=1)
+    assert g["iters"] == e["iters"] and g["model"][6] == e["model"][6]
+    assert np.all(rel(g["model"][7:11], e["model"][7:11]) < REL_EXACT)
+
+
+@pytest.mark.parametrize("group", [1, 4, 37, 148])
+def test_group_sizes_agree(group, oracle_port):
+    import better_flow_b200 as bf
+    sl = slices_240(61, 0.01, 1)[0]
+    c = bf.Context(180, 240, 3, max_events=1 << 17, max_slices=8, device=0)
+    try:
+        c.set_option("group_size", group)
+        got = c.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=10)
+        exact = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=10, accum_mode=1)
+        assert got["iters"] == exact["iters"]
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < REL_EXACT)
+    finally:
+        c.close()
+
+
+def test_large_sensor(oracle_port):
+    import better_flow_b200 as bf
+    st = synth.make_stream(640, 480, 10e6, 0.02, seed=71)
+    sl = synth.cut_slices(st, 0.02)[0]
+    c = bf.Context(480, 640, 3, max_events=1 << 18, max_slices=4, device=0)
+    try:
+        got = c.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=10)
+        exact = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=10, rows=480, cols=640, accum_mode=1)
+        ref = oracle_port.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=10, rows=480, cols=640, accum_mode=0)
+        assert got["iters"] == exact["iters"] and got["model"][6] == exact["model"][6]
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < REL_EXACT)
+        assert np.all(rel(got["model"][7:9], ref["model"][7:9]) < REL_CONTRACT)
+    finally:
+        c.close()
