@@ -22,24 +22,25 @@
 // =================================================================================================
 
 struct __align__(16) Smem {
-    u64 p0[BF_PTILE_MAX_ELEMS];
-    u64 p1[BF_PTILE_MAX_ELEMS];
-    float a[BF_AR * BF_AC];
-    double red[(BF_NT / 32) * BF_NSUMS];
+    double red[BF_NW * BF_NSUMS];
+    unsigned short list[BF_LIST_CAP];
+    int scan[BF_NW];
     SliceDesc sd;
     BfGeom g;
     BfPack pk;
     BfProj proj;
     BfOpt opt;
     int cont;
-    int slice;
+    int guard;
     int minmax[6];
 };
 
 template <int SH>
-__device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank) {
+__device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
+                          int rank) {
     u64 *img0 = P.images + (size_t)group * 2 * P.img_elems;
     u64 *img1 = img0 + P.img_elems;
+    unsigned *flags = P.flags + (size_t)group * P.flag_elems;
     double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
     const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
 
@@ -57,13 +58,15 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     for (int iter = 0;; ++iter) {
         u64 *img_new = buf ? img1 : img0;
         u64 *img_old = buf ? img0 : img1;
-        event_pass(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new,
-                   iter > 0 ? img_old : nullptr, nullptr);
+        tag += 1;
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new,
+                       iter > 0 ? img_old : nullptr, nullptr, flags, tag);
         group_barrier(&ws->bar, bar_target, P.G);   // A: all splats of this iteration are in L2
 
         Acc acc;
         acc_zero(acc);
-        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, rank, P.G, S.p0, S.p1, S.a, nullptr, nullptr, nullptr);
+        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags, tag, rank, P.G, S.list, S.scan, nullptr,
+                              nullptr, nullptr);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
         group_barrier(&ws->bar, bar_target, P.G);   // B: all partial sums are visible
 
@@ -78,8 +81,8 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         buf ^= 1;
     }
     // Last re-projection of iteration_step (optimizer_rolling.h:340-344) + clearing of the live image.
-    event_pass(P, S.sd, S.g, S.pk, S.proj, rank, false, P.want_events != 0, nullptr, buf ? img1 : img0,
-               P.want_events ? P.nxy : nullptr);
+    event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, P.want_events != 0, nullptr, buf ? img1 : img0,
+                   P.want_events ? P.nxy : nullptr, flags, tag);
 }
 
 __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) {
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
     const int rank = blockIdx.x - group * P.G;
     GroupWs *ws = P.ws + group;
     unsigned bar_target = 0;
+    unsigned tag = P.tag_base;   // advanced once per splatting event pass, identically in every CTA of the group
     int parity = 0;
 
     for (;;) {
@@ -156,18 +160,18 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
             const int t_min = S.sd.n > 0 ? __ldcg(&bb[4]) : 0, t_max = S.sd.n > 0 ? __ldcg(&bb[5]) : 0;
             bf_make_geom(S.g, x_min, x_max, y_min, y_max, S.sd.scale);
             bf_make_pack(S.pk, S.sd.n, t_min, t_max);
-            S.slice = 0;
-            if (bf_guard_tiny(S.g, P.res_x, P.res_y)) S.slice = 1;         // :49-55
-            else if (S.sd.n < P.min_events) S.slice = 2;                   // :57-58
+            S.guard = 0;
+            if (bf_guard_tiny(S.g, P.res_x, P.res_y)) S.guard = 1;         // :49-55
+            else if (S.sd.n < P.min_events) S.guard = 2;                   // :57-58
         }
         __syncthreads();
-        const int guard = S.slice;
+        const int guard = S.guard;
 
         if (guard == 0) {
             switch (S.sd.scale) {
-                case 1: run_slice<0>(P, S, ws, bar_target, group, rank); break;
-                case 3: run_slice<1>(P, S, ws, bar_target, group, rank); break;
-                default: run_slice<2>(P, S, ws, bar_target, group, rank); break;
+                case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank); break;
+                case 3: run_slice<1>(P, S, ws, bar_target, tag, group, rank); break;
+                default: run_slice<2>(P, S, ws, bar_target, tag, group, rank); break;
             }
         } else if (threadIdx.x == 0) {
             bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
@@ -180,11 +184,11 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
                 bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
             }
             __syncthreads();
-            event_pass(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, nullptr, P.nxy);
+            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, nullptr, P.nxy, nullptr, 0u);
         } else if (guard != 0 && P.want_events) {
             BfProj none;
             none.dnx = none.dny = none.cx = none.cy = none.div = none.s = 0; none.c = 1;
-            event_pass(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, nullptr, P.nxy);
+            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, nullptr, P.nxy, nullptr, 0u);
         }
         __syncthreads();
 
@@ -217,19 +221,27 @@ struct StageParams {
     BfPack pk;
     u64 *img;
     int pitch;
+    unsigned *flags;
+    unsigned tag;
     double *partials;
     float *out_img, *out_gx, *out_gy;
     double *out7;
 };
 
 // AccelLib::get_time_img_cpu's splat loop (accel_lib.h:151-166) as point splats.
+template <int SH>
 __global__ void bf_stage_splat_kernel(const StageParams P, int clear) {
+    const int n_ci = (P.g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (P.g.cols + CellCfg<SH>::CW - 1) / CellCfg<SH>::CW;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
         if (P.noise && P.noise[i]) continue;
-        const long long o = event_pixel(P.pr_x[i], P.pr_y[i], P.g, P.pitch);
-        if (o < 0) continue;
+        int x, y;
+        if (!event_pixel(P.pr_x[i], P.pr_y[i], P.g, x, y)) continue;
+        const long long o = pixel_offset(x, y, P.pitch);
         if (clear) P.img[o] = 0ull;
-        else atomicAdd(P.img + o, bf_pack_value(P.pk, P.t[i]));
+        else {
+            atomicAdd(P.img + o, bf_pack_value(P.pk, P.t[i]));
+            mark_cells<SH>(P.flags, P.tag, x, y, n_ci, n_cj);
+        }
     }
 }
 
@@ -239,8 +251,8 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StagePar
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     Acc acc;
     acc_zero(acc);
-    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, blockIdx.x, gridDim.x, S.p0, S.p1, S.a, P.out_img,
-                         P.out_gx, P.out_gy);
+    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, P.flags, P.tag, blockIdx.x, gridDim.x, S.list, S.scan,
+                         P.out_img, P.out_gx, P.out_gy);
     acc_block_reduce(acc, S.red, P.partials + blockIdx.x * BF_NSUMS);
 }
 
@@ -329,6 +341,9 @@ struct bf_ctx {
     double *d_partials = nullptr;
     u64 *d_images = nullptr;
     size_t images_bytes = 0;
+    unsigned *d_flags = nullptr;
+    long long flag_elems = 0;
+    unsigned launch_seq = 0;     // tag_base = launch_seq << 20; flags are re-zeroed when it wraps
     // stage scratch
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -369,6 +384,18 @@ static int pick_group(bf_ctx *c) {
     return G;
 }
 
+// Every launch gets a fresh range of 2^20 generation tags; when the 12-bit sequence wraps the flag
+// arrays are cleared so that an old tag can never alias a new one.
+static int next_tag_base(bf_ctx *c, unsigned *tag_base) {
+    c->launch_seq += 1;
+    if (c->launch_seq >= 4096u) {
+        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)c->n_groups * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+        c->launch_seq = 1;
+    }
+    *tag_base = c->launch_seq << 20;
+    return BF_OK;
+}
+
 static int configure(bf_ctx *c) {
     const int G = pick_group(c);
     const int n_groups = std::max(1, c->sms / G);
@@ -377,12 +404,16 @@ static int configure(bf_ctx *c) {
     if (c->d_images) cudaFree(c->d_images);
     if (c->d_ctrl) cudaFree(c->d_ctrl);
     if (c->d_partials) cudaFree(c->d_partials);
-    c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr;
+    if (c->d_flags) cudaFree(c->d_flags);
+    c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr; c->d_flags = nullptr;
     c->G = G;
     c->n_groups = n_groups;
     c->images_bytes = (size_t)n_groups * 2 * (size_t)c->img_elems * sizeof(u64);
     CU(cudaMalloc(&c->d_images, c->images_bytes));
     CU(cudaMemsetAsync(c->d_images, 0, c->images_bytes, c->stream));
+    CU(cudaMalloc(&c->d_flags, (size_t)n_groups * (size_t)c->flag_elems * sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->d_flags, 0, (size_t)n_groups * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+    c->launch_seq = 0;
     c->ctrl_bytes = 256 + (size_t)n_groups * sizeof(GroupWs);
     CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
     CU(cudaMalloc(&c->d_partials, (size_t)n_groups * G * BF_NSUMS * sizeof(double)));
@@ -438,10 +469,14 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
 
     const int max_rows = max_scale * sensor_rows, max_cols = max_scale * sensor_cols;
-    c->rows_alloc = ((max_rows + BF_TR - 1) / BF_TR) * BF_TR + 2 * BF_BORDER;
-    c->pitch = ((max_cols + BF_TC - 1) / BF_TC) * BF_TC + 2 * BF_BORDER;
+    // every cell patch (8 + 2H rows x 32 cols, H <= 3) of every cell that intersects the image must lie
+    // inside the allocation: cells start at multiples of 8 rows / CW cols, patches extend H beyond.
+    c->rows_alloc = ((max_rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS) * BF_CELL_ROWS + 2 * BF_BORDER;
+    c->pitch = max_cols + 32 + 2 * BF_BORDER;
     c->pitch = (c->pitch + 15) & ~15;   // 128-byte rows
     c->img_elems = (long long)c->rows_alloc * c->pitch;
+    c->flag_elems = (long long)((max_rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS) * ((max_cols + BF_CW_MIN - 1) / BF_CW_MIN);
+    c->flag_elems = (c->flag_elems + 63) & ~63LL;
 
     if ((e = cudaMallocHost(&c->h_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMallocHost(events)", e);
     if ((e = cudaMallocHost(&c->h_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMallocHost(slices)", e);
@@ -464,7 +499,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
     cudaFree(c->d_events); cudaFree(c->d_pr); cudaFree(c->d_nxy); cudaFree(c->d_slices);
-    cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images);
+    cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
     cudaFree(c->d_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -589,6 +624,8 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
     P.queue = reinterpret_cast<int *>(c->d_ctrl);
     P.ws = reinterpret_cast<GroupWs *>(c->d_ctrl + 256);
     P.partials = c->d_partials; P.images = c->d_images; P.img_elems = c->img_elems; P.pitch = c->pitch;
+    P.flags = c->d_flags; P.flag_elems = c->flag_elems;
+    if ((rc = next_tag_base(c, &P.tag_base)) != BF_OK) return rc;
     P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
     void *args[] = {&P};
@@ -694,7 +731,7 @@ static int stage_image(bf_ctx *c, int n, const double *pr_x, const double *pr_y,
     if (!c || n < 0 || (n > 0 && (!pr_x || !pr_y || !t_ns))) return fail(BF_ERR_ARG, "stage: bad arguments");
     if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported", scale);
     const int rows = w + scale, cols = h + scale;
-    if (w < 0 || h < 0 || rows > c->rows_alloc - 2 * BF_BORDER || cols > c->pitch - 2 * BF_BORDER)
+    if (w < 0 || h < 0 || rows > c->max_scale * c->res_x || cols > c->max_scale * c->res_y)
         return fail(BF_ERR_ARG, "image %dx%d exceeds the context's capacity", rows, cols);
     CU(cudaSetDevice(c->device));
     int rc = configure(c);
@@ -726,11 +763,26 @@ static int stage_image(bf_ctx *c, int n, const double *pr_x, const double *pr_y,
     if (n > 0) { t_min = *std::min_element(t_ns, t_ns + n); t_max = *std::max_element(t_ns, t_ns + n); }
     bf_make_pack(S.pk, n, t_min, t_max);
     S.img = c->d_images; S.pitch = c->pitch;
+    S.flags = c->d_flags;
+    if ((rc = next_tag_base(c, &S.tag)) != BF_OK) return rc;
+    S.tag += 1;
     S.partials = (double *)(base + o_part);
     S.out_img = (float *)(base + o_img); S.out_gx = (float *)(base + o_gx); S.out_gy = (float *)(base + o_gy);
     S.out7 = (double *)(base + o_out7);
     const int sb = std::max(1, std::min(4 * c->sms, (n + 255) / 256));
-    if (n > 0) { bf_stage_splat_kernel<<<sb, 256, 0, c->stream>>>(S, 0); c->launches++; }
+    // the image pass only visits live cells: everything else of the outputs is zero
+    CU(cudaMemsetAsync(base + o_img, 0, P * 4, c->stream));
+    CU(cudaMemsetAsync(base + o_gx, 0, P * 4, c->stream));
+    CU(cudaMemsetAsync(base + o_gy, 0, P * 4, c->stream));
+    auto splat = [&](int clear) {
+        switch (scale) {
+            case 1: bf_stage_splat_kernel<0><<<sb, 256, 0, c->stream>>>(S, clear); break;
+            case 3: bf_stage_splat_kernel<1><<<sb, 256, 0, c->stream>>>(S, clear); break;
+            default: bf_stage_splat_kernel<2><<<sb, 256, 0, c->stream>>>(S, clear); break;
+        }
+        c->launches++;
+    };
+    if (n > 0) splat(0);
     switch (scale) {
         case 1: bf_stage_image_kernel<0><<<grid, BF_NT, smem_bytes(), c->stream>>>(S); break;
         case 3: bf_stage_image_kernel<1><<<grid, BF_NT, smem_bytes(), c->stream>>>(S); break;
@@ -738,7 +790,7 @@ static int stage_image(bf_ctx *c, int n, const double *pr_x, const double *pr_y,
     }
     bf_stage_finish_kernel<<<1, 32, 0, c->stream>>>(S, grid);
     c->launches += 2;
-    if (n > 0) { bf_stage_splat_kernel<<<sb, 256, 0, c->stream>>>(S, 1); c->launches++; }   // restore the all-zero image
+    if (n > 0) splat(1);   // restore the all-zero image
     CU(cudaGetLastError());
     if (out_img) CU(cudaMemcpyAsync(out_img, S.out_img, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (out_gx) CU(cudaMemcpyAsync(out_gx, S.out_gx, P * 4, cudaMemcpyDeviceToHost, c->stream));

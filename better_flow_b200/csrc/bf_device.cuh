@@ -7,9 +7,12 @@
 //            (count | sum of t) at its centre pixel with one 64-bit integer atomic.  The
 //            reference's s x s splat (accel_lib.h:160-165) is recovered exactly in the image pass
 //            as an s x s box sum of the point image (integer sums are associative).  A zero border
-//            of BF_BORDER pixels surrounds the image so tile loads never need bounds checks.
+//            of BF_BORDER pixels surrounds the image so patch loads never need bounds checks.
 //   Two such images per CTA group: iteration k splats into image k&1 while the events clear
 //   their iteration k-1 pixels in the other one, so the image pass is read-only.
+//   flags    u32[cells]         one generation tag per 8 x (32-2H) pixel cell: an event stamps the
+//            current iteration's tag on every cell whose haloed patch contains its pixel; the image
+//            pass visits only cells carrying the current tag (the image is 1-5 % occupied).
 //
 // Reference paths are relative to /root/reference/better_flow_core/.
 #pragma once
@@ -19,25 +22,25 @@
 
 #include "bf_logic.h"
 
-// ---- compile-time tiling ------------------------------------------------------------------------
+// ---- compile-time geometry -------------------------------------------------------------------
 #define BF_NT 512              // threads per CTA (16 warps)
-#define BF_TR 30               // output rows per tile
-#define BF_TC 126              // output cols per tile
-#define BF_AR (BF_TR + 2)      // mean-time tile rows (1-pixel halo for the 3x3 Scharr)
-#define BF_AC (BF_TC + 2)      // = 128: one column per thread, 4 row strips of 8
-#define BF_STRIP 8
-#define BF_BORDER 4            // zero border of the stored image (>= scale/2 + 1 + alignment slack)
+#define BF_NW (BF_NT / 32)
+#define BF_BORDER 4            // zero border of the stored image (>= scale/2 + 1)
+#define BF_CELL_ROWS 8         // output rows per cell
+#define BF_LIST_CAP 4096       // active-cell list entries per scan chunk
 
 typedef unsigned long long u64;
 
-template <int SH> struct TileCfg {
-    static constexpr int H = SH + 1;                        // halo of the point tile: box radius + Scharr radius
-    static constexpr int OFF = (BF_BORDER - H) & 1;         // extra left column so rows start 16-B aligned
-    static constexpr int PR = BF_TR + 2 * H;                // point-tile rows
-    static constexpr int PW = BF_TC + 2 * H + 2 * OFF;      // point-tile cols (even)
-    static constexpr int CHUNKS = PR * (PW / 2);            // 16-byte chunks per tile
+// The image pass works on CELLS: 8 output rows x (32 - 2H) output columns, H = scale/2 + 1 being the
+// halo needed by the box sum (scale/2) plus the 3x3 Scharr (1).  A warp owns a cell: lane l holds
+// column l of the (8 + 2H) x 32 point patch in registers, so horizontal neighbours are shuffles.
+template <int SH> struct CellCfg {
+    static constexpr int H = SH + 1;
+    static constexpr int PR = BF_CELL_ROWS + 2 * H;   // patch rows held per lane
+    static constexpr int AR = BF_CELL_ROWS + 2;       // mean-time rows (1-row halo for Scharr)
+    static constexpr int CW = 32 - 2 * H;             // output columns per cell
 };
-#define BF_PTILE_MAX_ELEMS (36 * 134)                       // TileCfg<2>: PR=36, PW=134
+#define BF_CW_MIN 26   // CellCfg<2>::CW, for sizing the flag array
 
 struct SliceDesc {
     long long ev_off;   // first event of the slice in the batch arrays
@@ -71,6 +74,9 @@ struct KParams {
     u64 *images;             // [n_groups][2][img_elems]
     long long img_elems;
     int pitch;               // elements per stored image row
+    unsigned *flags;         // [n_groups][flag_elems] per-cell generation tags
+    long long flag_elems;
+    unsigned tag_base;       // launch sequence number << 20: tags are never reused, so flags need no clearing
     int G;                   // CTAs per group
     int res_x, res_y;        // sensor rows / cols
     int min_events;          // 1000 (optimizer_rolling.h:57)
@@ -86,14 +92,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {
     uint2 v;
@@ -142,14 +140,31 @@ __device__ __forceinline__ void project_event(double &prx, double &pry, double &
 }
 
 // Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158).
-// Returns the element offset into the stored (bordered) image, or -1 when the splat is rejected.
-__device__ __forceinline__ long long event_pixel(double prx, double pry, const BfGeom &g, int pitch) {
+// Returns false when the splat is rejected; x, y are un-bordered image coordinates.
+__device__ __forceinline__ bool event_pixel(double prx, double pry, const BfGeom &g, int &x, int &y) {
     const double fx = __dadd_rn(__dmul_rn(prx, (double)g.scale), (double)g.x_sh);
     const double fy = __dadd_rn(__dmul_rn(pry, (double)g.scale), (double)g.y_sh);
-    if (!(fx == fx) || !(fy == fy)) return -1;   // x86 cvttsd2si(NaN) = INT_MIN -> rejected
-    const int x = (int)fx, y = (int)fy;          // truncation toward zero; out-of-range saturates -> rejected
-    if ((x >= g.w + g.half) || (x < g.half) || (y >= g.h + g.half) || (y < g.half)) return -1;
+    if (!(fx == fx) || !(fy == fy)) return false;   // x86 cvttsd2si(NaN) = INT_MIN -> rejected
+    x = (int)fx;                                    // truncation toward zero; out-of-range saturates -> rejected
+    y = (int)fy;
+    return !((x >= g.w + g.half) || (x < g.half) || (y >= g.h + g.half) || (y < g.half));
+}
+__device__ __forceinline__ long long pixel_offset(int x, int y, int pitch) {
     return (long long)(x + BF_BORDER) * pitch + (y + BF_BORDER);
+}
+
+// Stamp `tag` on every cell whose haloed patch contains pixel (x, y): at most 2 x 2 cells.
+template <int SH>
+__device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x, int y, int n_ci, int n_cj) {
+    typedef CellCfg<SH> C;
+    const int i0 = max(0, (x - C::H) >> 3), i1 = min(n_ci - 1, (x + C::H) >> 3);
+    const int j0 = max(0, (y - C::H) / C::CW), j1 = min(n_cj - 1, (y + C::H) / C::CW);
+    flags[i0 * n_cj + j0] = tag;
+    if (j1 != j0) flags[i0 * n_cj + j1] = tag;
+    if (i1 != i0) {
+        flags[i1 * n_cj + j0] = tag;
+        if (j1 != j0) flags[i1 * n_cj + j1] = tag;
+    }
 }
 
 // ---- event pass: clear old pixel, re-project, splat --------------------------------------------
@@ -160,14 +175,17 @@ __device__ __forceinline__ long long event_pixel(double prx, double pry, const B
 //   img_new   : image receiving this iteration's splats (may be null: final pass)
 //   img_old   : image holding the previous iteration's splats, cleared here (may be null)
 //   out_nxy   : when non-null, nx/ny are written (final pass for writeout_events)
+template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, bool first, bool project, u64 *img_new,
-                           u64 *img_old, double2 *out_nxy) {
+                           u64 *img_old, double2 *out_nxy, unsigned *flags, unsigned tag) {
+    typedef CellCfg<SH> C;
     const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
     const int lo = rank * per;
     const int hi = min(sd.n, lo + per);
     const bf_event *ev = P.events + sd.ev_off;
     double2 *pr = P.pr + sd.ev_off;
+    const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
     for (int i = lo + (int)threadIdx.x; i < hi; i += BF_NT) {
         const uint2 e = ld_nc_u32x2(ev + i);
         const unsigned frx_u = e.x & 0xffffu;
@@ -178,17 +196,15 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         double prx, pry;
         if (first) { prx = (double)frx_u; pry = (double)fry_u; }
         else { const double2 s = pr[i]; prx = s.x; pry = s.y; }
-        if (img_old != nullptr && !noise) {
-            const long long o = event_pixel(prx, pry, g, P.pitch);
-            if (o >= 0) img_old[o] = 0ull;
-        }
+        int x, y;
+        if (img_old != nullptr && !noise && event_pixel(prx, pry, g, x, y)) img_old[pixel_offset(x, y, P.pitch)] = 0ull;
         double ex = 0.0, ey = 0.0;
         if (project) project_event(prx, pry, ex, ey, (float)frx_u, (float)fry_u, (float)t, q);
         if (project || first) pr[i] = make_double2(prx, pry);
         if (out_nxy != nullptr) out_nxy[sd.ev_off + i] = make_double2(ex, ey);
-        if (img_new != nullptr && !noise) {
-            const long long o = event_pixel(prx, pry, g, P.pitch);
-            if (o >= 0) atomicAdd(img_new + o, bf_pack_value(pk, t));
+        if (img_new != nullptr && !noise && event_pixel(prx, pry, g, x, y)) {
+            atomicAdd(img_new + pixel_offset(x, y, P.pitch), bf_pack_value(pk, t));
+            mark_cells<SH>(flags, tag, x, y, n_ci, n_cj);
         }
     }
 }
@@ -205,98 +221,75 @@ __device__ __forceinline__ void acc_zero(Acc &a) {
     a.sgx = a.sgy = a.sigx = a.sjgx = a.sigy = a.sjgy = 0.0;
 }
 
-// Issue the cp.async loads of one point tile (with halo) into shared memory.
-template <int SH>
-__device__ __forceinline__ void tile_load(u64 *sP, const u64 *img, int pitch, int tile_r, int tile_c) {
-    typedef TileCfg<SH> C;
-    const long long base = (long long)(tile_r * BF_TR + BF_BORDER - C::H) * pitch +
-                           (tile_c * BF_TC + BF_BORDER - C::H - C::OFF);
-    constexpr int CPR = C::PW / 2;   // 16-byte chunks per row
-    for (int k = threadIdx.x; k < C::CHUNKS; k += BF_NT) {
-        const int r = k / CPR, c = k - r * CPR;
-        cp_async16(sP + r * C::PW + 2 * c, img + base + (long long)r * pitch + 2 * c);
-    }
-}
-
-// Mean-timestamp tile from the point tile: s x s box sum of packed words (separable, rolling over
-// rows), then unpack -> (sum_t, count) -> f32 mean.  Thread = (row strip, column).
-template <int SH>
-__device__ __forceinline__ void tile_mean(float *sA, const u64 *sP, const BfPack &pk) {
-    typedef TileCfg<SH> C;
-    constexpr int K = 2 * SH + 1;
-    const int strip = threadIdx.x >> 7;      // 0..3
-    const int ac = threadIdx.x & 127;        // 0..127
-    u64 win[K];
-#pragma unroll
-    for (int k = 0; k < BF_STRIP + 2 * SH; ++k) {
-        const int pr = strip * BF_STRIP + k;
-        u64 hs = 0;
-#pragma unroll
-        for (int d = 0; d < K; ++d) hs += sP[pr * C::PW + ac + C::OFF + d];
-        win[k % K] = hs;
-        if (k >= 2 * SH) {
-            u64 v = 0;
-#pragma unroll
-            for (int d = 0; d < K; ++d) v += win[d];
-            sA[(strip * BF_STRIP + k - 2 * SH) * BF_AC + ac] = (v != 0ull) ? bf_unpack_avg(pk, v) : 0.0f;
-        }
-    }
-}
-
 // `p > 0.000001` with p an f32 promoted to f64 (object_model.cpp:20,114; accel_lib.h:534,599):
 // 1e-6f is the largest f32 below the f64 literal 1e-6, so the f32 compare is equivalent.
 #define BF_OCC(v) ((v) > 1e-6f)
 
-// AccelLib::sobel_point's live part (accel_lib.h:594-605): column-major tap order, f32 multiply
-// then f32 add, each rounded.  a(dr, dc) reads the mean-time tile around the centre.
-__device__ __forceinline__ bool scharr_at(const float *c, float &gx, float &gy) {
-    const float v00 = c[-BF_AC - 1], v01 = c[-1], v02 = c[BF_AC - 1];      // column j-1: rows i-1, i, i+1
-    const float v10 = c[-BF_AC], v12 = c[BF_AC];                            // column j
-    const float v20 = c[-BF_AC + 1], v21 = c[1], v22 = c[BF_AC + 1];      // column j+1
-    if (!(BF_OCC(v00) && BF_OCC(v01) && BF_OCC(v02) && BF_OCC(v10) && BF_OCC(v12) && BF_OCC(v20) &&
-          BF_OCC(v21) && BF_OCC(v22)))
-        return false;
-    float a = __fmul_rn(v00, 3.0f);
-    a = __fadd_rn(a, __fmul_rn(v02, -3.0f));
-    a = __fadd_rn(a, __fmul_rn(v10, 10.0f));
-    a = __fadd_rn(a, __fmul_rn(v12, -10.0f));
-    a = __fadd_rn(a, __fmul_rn(v20, 3.0f));
-    a = __fadd_rn(a, __fmul_rn(v22, -3.0f));
-    float b = __fmul_rn(v00, 3.0f);
-    b = __fadd_rn(b, __fmul_rn(v01, 10.0f));
-    b = __fadd_rn(b, __fmul_rn(v02, 3.0f));
-    b = __fadd_rn(b, __fmul_rn(v20, -3.0f));
-    b = __fadd_rn(b, __fmul_rn(v21, -10.0f));
-    b = __fadd_rn(b, __fmul_rn(v22, -3.0f));
-    gx = a;
-    gy = b;
-    return true;
-}
-
-// Scharr + reduction over the TR x TC output pixels of a tile (ObjectModel::center_of_mass and
-// ObjectModel::compute fused, object_model.cpp:103-126,4-39).  When out_* are non-null the mean
-// image / gradient images are also materialised (stage-level API and debug images only).
-template <bool MATERIALISE>
-__device__ __forceinline__ void tile_reduce(Acc &acc, const float *sA, int tile_r, int tile_c, int rows,
-                                            int cols, int i0, int j0, float *out_img, float *out_gx,
-                                            float *out_gy) {
-    const int strip = threadIdx.x >> 7;
-    const int oc = threadIdx.x & 127;
-    if (oc >= BF_TC) return;
-    const int j = tile_c * BF_TC + oc;
+// One cell, one warp.  Lane l holds column l of the point patch: PR rows of packed words.
+//   vertical box sum   (registers)          v[r]  = sum_{|d|<=SH} P[r+d]
+//   horizontal box sum (shuffles)           a[r]  = sum_{|d|<=SH} v[r] @ lane l+d
+//   unpack -> mean time f32                 A[r], r = 0..AR-1   (row ci*8 - 1 + r of the image)
+//   Scharr (accel_lib.h:594-605) + sums     lanes H..31-H, rows 1..8
+// Integer packed sums commute, so this equals the reference's per-event s x s splat exactly.
+template <int SH, bool MATERIALISE>
+__device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, int ci,
+                                             int cj, int rows, int cols, int i0, int j0, float *out_img,
+                                             float *out_gx, float *out_gy) {
+    typedef CellCfg<SH> C;
+    const int lane = threadIdx.x & 31;
+    const u64 *p = img + (long long)(ci * BF_CELL_ROWS - C::H + BF_BORDER) * pitch +
+                   (cj * C::CW - C::H + BF_BORDER + lane);
+    u64 P[C::PR];
 #pragma unroll
-    for (int k = 0; k < BF_STRIP; ++k) {
-        const int orow = strip * BF_STRIP + k;
-        if (orow >= BF_TR) break;
-        const int i = tile_r * BF_TR + orow;
-        const float *c = sA + (orow + 1) * BF_AC + (oc + 1);
-        const float v = *c;
+    for (int r = 0; r < C::PR; ++r) P[r] = __ldcg(p + (long long)r * pitch);
+
+    float A[C::AR];
+#pragma unroll
+    for (int r = 0; r < C::AR; ++r) {
+        u64 v = 0;
+#pragma unroll
+        for (int d = 0; d <= 2 * SH; ++d) v += P[r + d];      // patch rows r .. r+2SH  <->  image rows centred on A row r
+        u64 a = v;
+#pragma unroll
+        for (int d = 1; d <= SH; ++d) {
+            a += __shfl_up_sync(0xffffffffu, v, d);
+            a += __shfl_down_sync(0xffffffffu, v, d);
+        }
+        A[r] = (a != 0ull) ? bf_unpack_avg(pk, a) : 0.0f;
+    }
+    // lanes whose +-SH neighbours fall outside the warp hold garbage in A; they are never outputs
+    // (outputs are lanes H..31-H) nor neighbours of outputs (lanes H-1..32-H need lanes 0..31 only).
+    const bool out_lane = (lane >= C::H) && (lane < 32 - C::H);
+    const int j = cj * C::CW + lane - C::H;
+    float L0 = __shfl_up_sync(0xffffffffu, A[0], 1), R0 = __shfl_down_sync(0xffffffffu, A[0], 1);
+    float L1 = __shfl_up_sync(0xffffffffu, A[1], 1), R1 = __shfl_down_sync(0xffffffffu, A[1], 1);
+#pragma unroll
+    for (int r = 1; r <= BF_CELL_ROWS; ++r) {
+        const float L2 = __shfl_up_sync(0xffffffffu, A[r + 1], 1), R2 = __shfl_down_sync(0xffffffffu, A[r + 1], 1);
+        const int i = ci * BF_CELL_ROWS + r - 1;
+        const float v = A[r];
         float gx = 0.0f, gy = 0.0f;
-        if (BF_OCC(v)) {
+        if (out_lane && BF_OCC(v)) {
             acc.cnt += 1;
             acc.si += i;
             acc.sj += j;
-            if (scharr_at(c, gx, gy)) {
+            // taps: v(k,l) = T[row-1+l][col-1+k]; column j-1 = (L0,L1,L2), j = (A[r-1],.,A[r+1]), j+1 = (R0,R1,R2)
+            if (BF_OCC(L0) && BF_OCC(L1) && BF_OCC(L2) && BF_OCC(A[r - 1]) && BF_OCC(A[r + 1]) && BF_OCC(R0) &&
+                BF_OCC(R1) && BF_OCC(R2)) {
+                float a = __fmul_rn(L0, 3.0f);
+                a = __fadd_rn(a, __fmul_rn(L2, -3.0f));
+                a = __fadd_rn(a, __fmul_rn(A[r - 1], 10.0f));
+                a = __fadd_rn(a, __fmul_rn(A[r + 1], -10.0f));
+                a = __fadd_rn(a, __fmul_rn(R0, 3.0f));
+                a = __fadd_rn(a, __fmul_rn(R2, -3.0f));
+                float b = __fmul_rn(L0, 3.0f);
+                b = __fadd_rn(b, __fmul_rn(L1, 10.0f));
+                b = __fadd_rn(b, __fmul_rn(L2, 3.0f));
+                b = __fadd_rn(b, __fmul_rn(R0, -3.0f));
+                b = __fadd_rn(b, __fmul_rn(R1, -10.0f));
+                b = __fadd_rn(b, __fmul_rn(R2, -3.0f));
+                gx = a;
+                gy = b;
                 const double di = (double)(i - i0), dj = (double)(j - j0);
                 const double dgx = (double)gx, dgy = (double)gy;
                 acc.sgx += dgx;
@@ -308,13 +301,14 @@ __device__ __forceinline__ void tile_reduce(Acc &acc, const float *sA, int tile_
             }
         }
         if (MATERIALISE) {
-            if (i < rows && j < cols) {
+            if (out_lane && i < rows && j < cols) {
                 const size_t o = (size_t)i * cols + j;
                 if (out_img) out_img[o] = v;
                 if (out_gx) out_gx[o] = gx;
                 if (out_gy) out_gy[o] = gy;
             }
         }
+        L0 = L1; L1 = L2; R0 = R1; R1 = R2;
     }
 }
 
@@ -324,9 +318,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// CTA-wide reduction of the per-thread accumulators; thread 0 writes BF_NSUMS doubles to `slot`.
+// CTA-wide reduction of the per-thread accumulators; BF_NSUMS doubles are written to `slot`.
 // Fixed association order => bit-reproducible.
-__device__ void acc_block_reduce(const Acc &a, double *sred /* [16][BF_NSUMS] */, double *slot) {
+__device__ void acc_block_reduce(const Acc &a, double *sred /* [BF_NW][BF_NSUMS] */, double *slot) {
     double v[BF_NSUMS] = {(double)a.cnt, (double)a.si, (double)a.sj, a.sgx, a.sgy, a.sigx, a.sjgx, a.sigy, a.sjgy};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -337,38 +331,58 @@ __device__ void acc_block_reduce(const Acc &a, double *sred /* [16][BF_NSUMS] */
     __syncthreads();
     if (threadIdx.x < BF_NSUMS) {
         double s = 0.0;
-        for (int w = 0; w < BF_NT / 32; ++w) s += sred[w * BF_NSUMS + threadIdx.x];
+        for (int w = 0; w < BF_NW; ++w) s += sred[w * BF_NSUMS + threadIdx.x];
         slot[threadIdx.x] = s;
     }
     __syncthreads();
 }
 
-// Image pass of one CTA: tiles rank, rank+G, ... of the slice's image, double-buffered through
-// shared memory with cp.async.
+// Image pass of one CTA.  The cell flags are scanned in chunks of BF_LIST_CAP; every CTA of the
+// group builds the same compacted list of live cells (index order => deterministic) and its
+// warps take entries  rank*NW + warp, += G*NW.  No CTA barrier inside the cell loop.
 template <int SH, bool MATERIALISE>
-__device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk, int rank,
-                           int G, u64 *sP0, u64 *sP1, float *sA, float *out_img, float *out_gx, float *out_gy) {
-    const int tiles_c = (g.cols + BF_TC - 1) / BF_TC;
-    const int tiles_r = (g.rows + BF_TR - 1) / BF_TR;
-    const int n_tiles = tiles_r * tiles_c;
+__device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
+                           const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
+                           int *scan, float *out_img, float *out_gx, float *out_gy) {
+    typedef CellCfg<SH> C;
+    const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
+    const int n_cells = n_ci * n_cj;
     const int i0 = g.rows / 2, j0 = g.cols / 2;
-    int t = rank;
-    if (t < n_tiles) tile_load<SH>(sP0, img, pitch, t / tiles_c, t % tiles_c);
-    cp_async_commit();
-    int buf = 0;
-    for (; t < n_tiles; t += G) {
-        const int tn = t + G;
-        if (tn < n_tiles) tile_load<SH>(buf ? sP0 : sP1, img, pitch, tn / tiles_c, tn % tiles_c);
-        cp_async_commit();
-        cp_async_wait<1>();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PER = BF_LIST_CAP / BF_NT;   // flags per thread per chunk
+    for (int base = 0; base < n_cells; base += BF_LIST_CAP) {
+        // ---- compact the live cells of this chunk -----------------------------------------------
+        unsigned live = 0;
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int c = base + (int)threadIdx.x * PER + k;
+            if (c < n_cells && __ldcg(flags + c) == tag) { live |= 1u << k; ++mine; }
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        __syncthreads();   // previous chunk's list fully consumed
+        if (lane == 31) scan[warp] = incl;
         __syncthreads();
-        tile_mean<SH>(sA, buf ? sP1 : sP0, pk);
+        int off = incl - mine;
+        for (int w = 0; w < warp; ++w) off += scan[w];
+        int total = 0;
+        for (int w = 0; w < BF_NW; ++w) total += scan[w];
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (live & (1u << k)) list[off++] = (unsigned short)((int)threadIdx.x * PER + k);
         __syncthreads();
-        tile_reduce<MATERIALISE>(acc, sA, t / tiles_c, t % tiles_c, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
-        __syncthreads();
-        buf ^= 1;
+        // ---- process them ---------------------------------------------------------------------------
+        for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+            const int c = base + (int)list[k];
+            const int ci = c / n_cj, cj = c - ci * n_cj;
+            cell_process<SH, MATERIALISE>(acc, img, pitch, pk, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+        }
     }
-    cp_async_wait<0>();
 }
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):

@@ -89,7 +89,13 @@ BF_HD float bf_unpack_avg(const BfPack &p, unsigned long long v) {
     const unsigned long long cnt = v >> p.cnt_shift;
     if (cnt == 0) return 0.0f;
     const long long sum = (long long)((v & p.sum_mask) << p.q) + (long long)cnt * (long long)p.t_min;
-    const float s = (float)((double)sum / 1000000000.0);
+    // sum / 1e9 as multiply-by-reciprocal + one fma correction step: equal to the correctly rounded
+    // quotient for every integer dividend tried (2e9 random |a| < 2^53, tools/ in DESIGN.md) and
+    // ~10x cheaper than an IEEE fp64 divide on the GPU.
+    const double a = (double)sum;
+    const double q0 = a * 1e-9;
+    const double qd = fma(fma(-1000000000.0, q0, a), 1e-9, q0);
+    const float s = (float)qd;
     return s / (float)cnt;
 }
 
