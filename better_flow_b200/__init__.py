@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbf_cuda.so")
 
+RESULT_BYTES = 160  # sizeof(bf_slice_result), checked in load()
 RC_OK, RC_SKIPPED, RC_ITER_CAP, RC_DEGENERATE = 0, 1, 2, 3
 FLAG_ALL_NOISE, FLAG_T_QUANTISED = 1, 2
 EVENT_NOISE = 0x8000
@@ -56,6 +57,7 @@ ABI_SYMBOLS = (
     "bf_batch_staging", "bf_batch_add_staged", "bf_batch_upload", "bf_batch_launch", "bf_batch_download",
     "bf_batch_sync", "bf_batch_run", "bf_batch_time_launches", "bf_ctx_launch_count", "bf_batch_size",
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
+    "bf_ctx_set_stream", "bf_batch_results_device",
 )
 
 _lib = None
@@ -84,6 +86,8 @@ def load() -> C.CDLL:
         lib.bf_ctx_get_option.restype = C.c_longlong
         lib.bf_ctx_launch_count.argtypes = [C.c_void_p]
         lib.bf_ctx_launch_count.restype = C.c_longlong
+        lib.bf_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.bf_batch_results_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
         lib.bf_batch_staging.restype = C.c_void_p
         lib.bf_batch_staging.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         lib.bf_batch_add_staged.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -107,6 +111,7 @@ def load() -> C.CDLL:
         lib.bf_project.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_double, C.c_double]
+        assert C.sizeof(SliceResult) == RESULT_BYTES and C.sizeof(Model) == 88
         _lib = lib
     return _lib
 
@@ -166,6 +171,17 @@ class Context:
 
     def get_option(self, key):
         return int(self.lib.bf_ctx_get_option(self.h, key.encode()))
+
+    def set_stream(self, cuda_stream_handle):
+        """Run on a caller-owned CUDA stream (integer handle, e.g. torch.cuda.Stream().cuda_stream)."""
+        self._chk(self.lib.bf_ctx_set_stream(self.h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def results_device(self):
+        """(device pointer, byte size) of the bf_slice_result records of the current batch."""
+        p = C.c_void_p(0)
+        n = C.c_longlong(0)
+        self._chk(self.lib.bf_batch_results_device(self.h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
 
     @property
     def launches(self):

@@ -235,7 +235,9 @@ __global__ void bf_stage_splat_kernel(const StageParams P, int clear) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
         if (P.noise && P.noise[i]) continue;
         int x, y;
-        if (!event_pixel(P.pr_x[i], P.pr_y[i], P.g, x, y)) continue;
+        PixelMap pm;
+        make_pixel_map(pm, P.g, P.pitch);
+        if (!event_pixel(P.pr_x[i], P.pr_y[i], pm, x, y)) continue;
         const long long o = pixel_offset(x, y, P.pitch);
         if (clear) P.img[o] = 0ull;
         else {
@@ -311,6 +313,7 @@ struct bf_ctx {
     long long max_events = 0;
     int max_slices = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // options
@@ -464,7 +467,8 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     c->sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { fail(BF_ERR_CUDA, "device lacks cooperative launch"); bf_ctx_destroy(c); return nullptr; }
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
 
@@ -503,7 +507,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaFree(c->d_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -531,6 +535,21 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
 }
 
 long long bf_ctx_launch_count(bf_ctx *c) { return c ? c->launches : 0; }
+
+int bf_ctx_set_stream(bf_ctx *c, void *cuda_stream) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return BF_OK;
+}
+
+int bf_batch_results_device(bf_ctx *c, void **dev_ptr, long long *bytes) {
+    if (!c || !dev_ptr || !bytes) return fail(BF_ERR_ARG, "bf_batch_results_device: null argument");
+    *dev_ptr = c->d_results;
+    *bytes = (long long)c->n_slices * (long long)sizeof(bf_slice_result);
+    return BF_OK;
+}
 
 int bf_batch_reset(bf_ctx *c) {
     if (!c) return fail(BF_ERR_ARG, "null context");
@@ -848,3 +867,7 @@ int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, con
 }
 
 }  // extern "C"
+
+static_assert(sizeof(bf_model) == 88, "bf_model must mirror ObjectModel's 11 scalars");
+static_assert(sizeof(bf_slice_result) == 160, "bf_slice_result layout is part of the ABI");
+static_assert(sizeof(bf_event) == 8, "bf_event is the 8-byte compact record");

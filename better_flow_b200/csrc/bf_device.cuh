@@ -139,15 +139,33 @@ __device__ __forceinline__ void project_event(double &prx, double &pry, double &
     pry = __dsub_rn((double)fry, div_const((double)__fmul_rn(ky, tf), 10000.0, 1.0 / 10000.0));
 }
 
-// Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158).
-// Returns false when the splat is rejected; x, y are un-bordered image coordinates.
-__device__ __forceinline__ bool event_pixel(double prx, double pry, const BfGeom &g, int &x, int &y) {
-    const double fx = __dadd_rn(__dmul_rn(prx, (double)g.scale), (double)g.x_sh);
-    const double fy = __dadd_rn(__dmul_rn(pry, (double)g.scale), (double)g.y_sh);
-    if (!(fx == fx) || !(fy == fy)) return false;   // x86 cvttsd2si(NaN) = INT_MIN -> rejected
-    x = (int)fx;                                    // truncation toward zero; out-of-range saturates -> rejected
+// Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158):
+//   int x = pr_x * scale + x_sh (f64, truncation toward zero), rejected unless half <= x < w + half.
+// The test is done on the f64 value before truncation, which is equivalent for integer bounds
+// (trunc(f) >= k  <=>  f >= k for k >= 1, f > -1 for k == 0;  trunc(f) < k  <=>  f < k for k >= 1)
+// and rejects NaN like x86's cvttsd2si(NaN) = INT_MIN does.
+struct PixelMap {
+    double sc, xs, ys;       // scale, x_sh, y_sh as f64
+    double xlo, xhi, ylo, yhi;
+    bool lo_open;            // half == 0: lower bound is the open interval (-1, ...)
+    int pitch;
+};
+__device__ __forceinline__ void make_pixel_map(PixelMap &m, const BfGeom &g, int pitch) {
+    m.sc = (double)g.scale; m.xs = (double)g.x_sh; m.ys = (double)g.y_sh;
+    m.lo_open = g.half == 0;
+    m.xlo = m.lo_open ? -1.0 : (double)g.half;
+    m.ylo = m.xlo;
+    m.xhi = (double)(g.w + g.half);
+    m.yhi = (double)(g.h + g.half);
+    m.pitch = pitch;
+}
+__device__ __forceinline__ bool event_pixel(double prx, double pry, const PixelMap &m, int &x, int &y) {
+    const double fx = __dadd_rn(__dmul_rn(prx, m.sc), m.xs);
+    const double fy = __dadd_rn(__dmul_rn(pry, m.sc), m.ys);
+    const bool ok = (m.lo_open ? (fx > m.xlo && fy > m.ylo) : (fx >= m.xlo && fy >= m.ylo)) && fx < m.xhi && fy < m.yhi;
+    x = (int)fx;
     y = (int)fy;
-    return !((x >= g.w + g.half) || (x < g.half) || (y >= g.h + g.half) || (y < g.half));
+    return ok;
 }
 __device__ __forceinline__ long long pixel_offset(int x, int y, int pitch) {
     return (long long)(x + BF_BORDER) * pitch + (y + BF_BORDER);
@@ -157,13 +175,16 @@ __device__ __forceinline__ long long pixel_offset(int x, int y, int pitch) {
 template <int SH>
 __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x, int y, int n_ci, int n_cj) {
     typedef CellCfg<SH> C;
-    const int i0 = max(0, (x - C::H) >> 3), i1 = min(n_ci - 1, (x + C::H) >> 3);
-    const int j0 = max(0, (y - C::H) / C::CW), j1 = min(n_cj - 1, (y + C::H) / C::CW);
-    flags[i0 * n_cj + j0] = tag;
-    if (j1 != j0) flags[i0 * n_cj + j1] = tag;
-    if (i1 != i0) {
-        flags[i1 * n_cj + j0] = tag;
-        if (j1 != j0) flags[i1 * n_cj + j1] = tag;
+    const int ci = x >> 3, cj = y / C::CW;
+    const int lx = x & 7, ly = y - cj * C::CW;
+    unsigned *f = flags + ci * n_cj + cj;
+    *f = tag;
+    const int dj = (ly < C::H && cj > 0) ? -1 : ((ly >= C::CW - C::H && cj + 1 < n_cj) ? 1 : 0);
+    const int di = (lx < C::H && ci > 0) ? -n_cj : ((lx >= BF_CELL_ROWS - C::H && ci + 1 < n_ci) ? n_cj : 0);
+    if (dj != 0) f[dj] = tag;
+    if (di != 0) {
+        f[di] = tag;
+        if (dj != 0) f[di + dj] = tag;
     }
 }
 
@@ -175,6 +196,42 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
 //   img_new   : image receiving this iteration's splats (may be null: final pass)
 //   img_old   : image holding the previous iteration's splats, cleared here (may be null)
 //   out_nxy   : when non-null, nx/ny are written (final pass for writeout_events)
+// Two events per thread per trip with all loads issued up front: the pass is latency-bound
+// (one L2 round trip per event otherwise), not bandwidth-bound.
+struct EventCtx {
+    PixelMap pm;
+    BfProj q;
+    int cnt_shift, tq, t_min;
+    int n_ci, n_cj;
+    bool first, project;
+    u64 *img_new, *img_old;
+    unsigned *flags;
+    unsigned tag;
+};
+
+template <int SH>
+__device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, double2 st, double2 *pr_slot, double2 *nxy_slot) {
+    const unsigned frx_u = e.x & 0xffffu;
+    const unsigned fry_raw = e.x >> 16;
+    const bool noise = (fry_raw & BF_EVENT_NOISE) != 0;
+    const unsigned fry_u = fry_raw & 0x7fffu;
+    const int t = (int)e.y;
+    double prx, pry;
+    if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }
+    else { prx = st.x; pry = st.y; }
+    int x, y;
+    if (c.img_old != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) c.img_old[pixel_offset(x, y, c.pm.pitch)] = 0ull;
+    double ex = 0.0, ey = 0.0;
+    if (c.project) project_event(prx, pry, ex, ey, (float)frx_u, (float)fry_u, (float)t, c.q);
+    if (c.project || c.first) *pr_slot = make_double2(prx, pry);
+    if (nxy_slot != nullptr) *nxy_slot = make_double2(ex, ey);
+    if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
+        const u64 dt = (u64)((long long)t - (long long)c.t_min);
+        atomicAdd(c.img_new + pixel_offset(x, y, c.pm.pitch), (1ull << c.cnt_shift) + (dt >> c.tq));
+        mark_cells<SH>(c.flags, c.tag, x, y, c.n_ci, c.n_cj);
+    }
+}
+
 template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, bool first, bool project, u64 *img_new,
@@ -182,30 +239,31 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     typedef CellCfg<SH> C;
     const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
     const int lo = rank * per;
-    const int hi = min(sd.n, lo + per);
-    const bf_event *ev = P.events + sd.ev_off;
-    double2 *pr = P.pr + sd.ev_off;
-    const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
-    for (int i = lo + (int)threadIdx.x; i < hi; i += BF_NT) {
-        const uint2 e = ld_nc_u32x2(ev + i);
-        const unsigned frx_u = e.x & 0xffffu;
-        const unsigned fry_raw = e.x >> 16;
-        const bool noise = (fry_raw & BF_EVENT_NOISE) != 0;
-        const unsigned fry_u = fry_raw & 0x7fffu;
-        const int t = (int)e.y;
-        double prx, pry;
-        if (first) { prx = (double)frx_u; pry = (double)fry_u; }
-        else { const double2 s = pr[i]; prx = s.x; pry = s.y; }
-        int x, y;
-        if (img_old != nullptr && !noise && event_pixel(prx, pry, g, x, y)) img_old[pixel_offset(x, y, P.pitch)] = 0ull;
-        double ex = 0.0, ey = 0.0;
-        if (project) project_event(prx, pry, ex, ey, (float)frx_u, (float)fry_u, (float)t, q);
-        if (project || first) pr[i] = make_double2(prx, pry);
-        if (out_nxy != nullptr) out_nxy[sd.ev_off + i] = make_double2(ex, ey);
-        if (img_new != nullptr && !noise && event_pixel(prx, pry, g, x, y)) {
-            atomicAdd(img_new + pixel_offset(x, y, P.pitch), bf_pack_value(pk, t));
-            mark_cells<SH>(flags, tag, x, y, n_ci, n_cj);
+    const int cnt = min(sd.n, lo + per) - lo;
+    if (cnt <= 0) return;
+    const bf_event *ev = P.events + sd.ev_off + lo;
+    double2 *pr = P.pr + sd.ev_off + lo;
+    double2 *nxy = out_nxy ? out_nxy + sd.ev_off + lo : nullptr;
+    EventCtx c;
+    make_pixel_map(c.pm, g, P.pitch);
+    c.q = q;
+    c.cnt_shift = pk.cnt_shift; c.tq = pk.q; c.t_min = pk.t_min;
+    c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
+    c.n_cj = (g.cols + C::CW - 1) / C::CW;
+    c.first = first; c.project = project; c.img_new = img_new; c.img_old = img_old; c.flags = flags; c.tag = tag;
+    for (int i = (int)threadIdx.x; i < cnt; i += 2 * BF_NT) {
+        const int k = i + BF_NT;
+        const bool two = k < cnt;
+        const uint2 e0 = ld_nc_u32x2(ev + i);
+        uint2 e1 = make_uint2(0u, 0u);
+        if (two) e1 = ld_nc_u32x2(ev + k);
+        double2 s0 = make_double2(0.0, 0.0), s1 = s0;
+        if (!first) {
+            s0 = pr[i];
+            if (two) s1 = pr[k];
         }
+        event_one<SH>(c, e0, s0, pr + i, nxy ? nxy + i : nullptr);
+        if (two) event_one<SH>(c, e1, s1, pr + k, nxy ? nxy + k : nullptr);
     }
 }
 

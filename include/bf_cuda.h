@@ -103,6 +103,11 @@ void bf_ctx_destroy(bf_ctx *ctx);
 int bf_ctx_set_option(bf_ctx *ctx, const char *key, long long value);
 long long bf_ctx_get_option(bf_ctx *ctx, const char *key);
 
+/* Run everything of this context on a caller-owned stream (a cudaStream_t passed as void*), e.g. the
+ * stream a host framework times with its own events or orders NCCL calls on.  NULL restores the
+ * context's private stream. */
+int bf_ctx_set_stream(bf_ctx *ctx, void *cuda_stream);
+
 /* ---- batched minimisation: N independent slices in one persistent launch -------------------
  * A "slice" is what DVS_flow::recompute hands to OptimizerRolling (dvs_flow.h:196-222):
  * events in iteration order, local times, scale, max_iter and an optional warm-start model. */
@@ -139,6 +144,11 @@ int bf_batch_run(bf_ctx *ctx, int want_events);
 int bf_batch_time_launches(bf_ctx *ctx, int reps, int want_events, float *ms);
 /* Number of kernels launched by this context so far. */
 long long bf_ctx_launch_count(bf_ctx *ctx);
+
+/* Device address and byte size of the result records of the current batch (bf_slice_result[n]),
+ * valid after bf_batch_launch: lets a multi-GPU caller hand them to its collective (NCCL gather of
+ * the per-slice flow) without a host round trip. */
+int bf_batch_results_device(bf_ctx *ctx, void **dev_ptr, long long *bytes);
 
 int bf_batch_size(bf_ctx *ctx);
 int bf_batch_result(bf_ctx *ctx, int slot, bf_slice_result *out);
