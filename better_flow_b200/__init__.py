@@ -57,7 +57,7 @@ ABI_SYMBOLS = (
     "bf_batch_staging", "bf_batch_add_staged", "bf_batch_upload", "bf_batch_launch", "bf_batch_download",
     "bf_batch_sync", "bf_batch_run", "bf_batch_time_launches", "bf_ctx_launch_count", "bf_batch_size",
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
-    "bf_ctx_set_stream", "bf_batch_results_device",
+    "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile",
 )
 
 _lib = None
@@ -182,6 +182,12 @@ class Context:
         n = C.c_longlong(0)
         self._chk(self.lib.bf_batch_results_device(self.h, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
+
+    def debug_profile(self):
+        out = np.zeros((1024, 16), dtype=np.int64)
+        self.lib.bf_debug_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = self._chk(self.lib.bf_debug_profile(self.h, _ptr(out), 1024))
+        return out[:n]
 
     @property
     def launches(self):

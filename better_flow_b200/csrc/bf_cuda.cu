@@ -54,6 +54,15 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     }
     __syncthreads();
 
+    long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
+    const bool prof = pf != nullptr && threadIdx.x == 0;
+    long long tc = prof ? clock64() : 0;
+#define PF_MARK(slot)                         \
+    if (prof) {                               \
+        const long long now_ = clock64();     \
+        pf[slot] += now_ - tc;                \
+        tc = now_;                            \
+    }
     int buf = 0;
     for (int iter = 0;; ++iter) {
         u64 *img_new = buf ? img1 : img0;
@@ -61,31 +70,54 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         tag += 1;
         event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new,
                        iter > 0 ? img_old : nullptr, nullptr, flags, tag);
-        group_barrier(&ws->bar, bar_target, P.G);   // A: all splats of this iteration are in L2
+        if (pf) __syncthreads();
+        PF_MARK(PF_EVENT);
+        {
+            const long long sp = group_barrier(&ws->bar, bar_target, P.G);   // A: all splats of this iteration are in L2
+            if (prof) pf[PF_BAR_A_SPIN] += sp;
+        }
+        PF_MARK(PF_BAR_A);
 
         Acc acc;
         acc_zero(acc);
         image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags, tag, rank, P.G, S.list, S.scan, nullptr,
                               nullptr, nullptr);
+        if (pf) __syncthreads();
+        PF_MARK(PF_CELLS);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
-        group_barrier(&ws->bar, bar_target, P.G);   // B: all partial sums are visible
+        PF_MARK(PF_REDUCE);
+        {
+            const long long sp = group_barrier(&ws->bar, bar_target, P.G);   // B: all partial sums are visible
+            if (prof) pf[PF_BAR_B_SPIN] += sp;
+        }
+        PF_MARK(PF_BAR_B);
 
         if (threadIdx.x < 32) {
             BfSums s;
-            group_sums(s, partials, P.G);
-            if (threadIdx.x == 0)
-                S.cont = bf_opt_advance(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj) ? 1 : 0;
+            group_sums(s, partials, P.G, pf ? pf + 14 : nullptr);
+            PF_MARK(PF_SCAN);   // (slot reused: time of the partial-sum gather)
+            const bool cont = opt_advance_warp(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj);
+            if (threadIdx.x == 0) S.cont = cont ? 1 : 0;
         }
         __syncthreads();
+        PF_MARK(PF_SERIAL);
+        if (prof) pf[PF_ITERS] += 1;
         if (!S.cont) break;
         buf ^= 1;
     }
     // Last re-projection of iteration_step (optimizer_rolling.h:340-344) + clearing of the live image.
     event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, P.want_events != 0, nullptr, buf ? img1 : img0,
                    P.want_events ? P.nxy : nullptr, flags, tag);
+    if (pf) __syncthreads();
+    PF_MARK(PF_FINAL);
+    if (prof) pf[PF_SLICES] += 1;
+#undef PF_MARK
 }
 
-__global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) {
+// MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
+// (twice the warps to hide L2 latency, at the price of a few spills).
+template <int MINB>
+__global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int group = blockIdx.x / P.G;
@@ -94,8 +126,11 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
     unsigned bar_target = 0;
     unsigned tag = P.tag_base;   // advanced once per splatting event pass, identically in every CTA of the group
     int parity = 0;
+    long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
+    const long long t_begin = pf ? clock64() : 0;
 
     for (;;) {
+        const long long t_pro = pf ? clock64() : 0;
         // ---- fetch the next slice for this group ------------------------------------------------
         if (rank == 0 && threadIdx.x == 0) {
             const int s = atomicAdd(P.queue, 1);
@@ -127,6 +162,7 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
                 ymin = min(ymin, fy); ymax = max(ymax, fy);
                 tmin = min(tmin, t); tmax = max(tmax, t);
             }
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
@@ -166,6 +202,7 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
         }
         __syncthreads();
         const int guard = S.guard;
+        if (pf && threadIdx.x == 0) pf[PF_PROLOGUE] += clock64() - t_pro;
 
         if (guard == 0) {
             switch (S.sd.scale) {
@@ -208,6 +245,7 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_minimize_kernel(const KParams P) 
         }
         parity ^= 1;
     }
+    if (pf && threadIdx.x == 0) pf[PF_TOTAL] += clock64() - t_begin;
 }
 
 // ---- stage-level kernels (AccelLib surface; same device functions as the persistent kernel) ----
@@ -317,10 +355,13 @@ struct bf_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // options
-    int opt_group = 0;          // 0 = auto
+    int opt_group = 0;          // CTAs per slice; 0 = auto (from the batch size)
+    int min_group = 4;          // smallest automatic group
+    int ctas_per_sm = 2;        // 1 or 2 resident CTAs per SM
+    long long image_budget_mb = 24576;   // cap on the point-image allocation
+    int n_groups_alloc = 0;
     int iter_cap = 20000;
     int min_events = 1000;
-    long long l2_budget_mb = 64;
 
     // geometry of the stored images
     int pitch = 0, rows_alloc = 0;
@@ -347,6 +388,8 @@ struct bf_ctx {
     unsigned *d_flags = nullptr;
     long long flag_elems = 0;
     unsigned launch_seq = 0;     // tag_base = launch_seq << 20; flags are re-zeroed when it wraps
+    long long *d_prof = nullptr; // debug phase counters
+    int profile = 0;
     // stage scratch
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -373,18 +416,30 @@ static int ensure_device() {
     return BF_OK;
 }
 
-static int pick_group(bf_ctx *c) {
-    int G = c->opt_group;
-    if (G <= 0) {
-        // as many groups as keep the live images (2 per group) inside the L2 budget
-        const double per_group_mb = 2.0 * (double)c->img_elems * 8.0 / 1048576.0;
-        int groups = (int)std::max(1.0, std::floor((double)c->l2_budget_mb / per_group_mb));
-        groups = std::min(groups, c->sms / 2);
-        if (groups < 1) groups = 1;
-        G = c->sms / groups;
-    }
-    G = std::max(1, std::min(G, c->sms));
-    return G;
+// Launch geometry.  slots = SMs x resident CTAs per SM.  A group of G CTAs works on one slice at a
+// time; the best G is the smallest that still keeps every slot busy: barriers and the serial GD
+// update cost a fixed ~10 us per iteration per group, so fewer CTAs per slice and more slices in
+// flight wins (measured: G=4 > 8 > 16 on DAVIS-240C), while a small batch wants all CTAs on its few
+// slices.  Buffers are allocated once for the largest group count (slots / min_group, capped by
+// the image-memory budget); G is then chosen per launch from the batch size.
+static int max_groups(bf_ctx *c) {
+    const int slots = c->sms * c->ctas_per_sm;
+    long long by_mem = (long long)((double)c->image_budget_mb * 1048576.0 / (2.0 * (double)c->img_elems * 8.0));
+    if (by_mem < 1) by_mem = 1;
+    int g = slots / std::max(1, c->min_group);
+    if (c->opt_group > 0) g = slots / std::min(slots, c->opt_group);
+    g = (int)std::min<long long>(std::max(1, g), by_mem);
+    return g;
+}
+
+static void pick_launch(bf_ctx *c, int n_slices, int *G, int *n_groups) {
+    const int slots = c->sms * c->ctas_per_sm;
+    int groups = c->n_groups_alloc;
+    if (c->opt_group <= 0) groups = std::min(groups, std::max(1, n_slices));
+    int g = std::max(1, slots / groups);
+    if (c->opt_group > 0) g = std::min(slots, std::max(c->opt_group, g));
+    *G = g;
+    *n_groups = std::min(groups, slots / g);
 }
 
 // Every launch gets a fresh range of 2^20 generation tags; when the 12-bit sequence wraps the flag
@@ -392,34 +447,35 @@ static int pick_group(bf_ctx *c) {
 static int next_tag_base(bf_ctx *c, unsigned *tag_base) {
     c->launch_seq += 1;
     if (c->launch_seq >= 4096u) {
-        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)c->n_groups * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)c->n_groups_alloc * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
         c->launch_seq = 1;
     }
     *tag_base = c->launch_seq << 20;
     return BF_OK;
 }
 
-static int configure(bf_ctx *c) {
-    const int G = pick_group(c);
-    const int n_groups = std::max(1, c->sms / G);
-    if (G == c->G && n_groups == c->n_groups && c->d_images) return BF_OK;
-    CU(cudaStreamSynchronize(c->stream));
-    if (c->d_images) cudaFree(c->d_images);
-    if (c->d_ctrl) cudaFree(c->d_ctrl);
-    if (c->d_partials) cudaFree(c->d_partials);
-    if (c->d_flags) cudaFree(c->d_flags);
-    c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr; c->d_flags = nullptr;
-    c->G = G;
-    c->n_groups = n_groups;
-    c->images_bytes = (size_t)n_groups * 2 * (size_t)c->img_elems * sizeof(u64);
-    CU(cudaMalloc(&c->d_images, c->images_bytes));
-    CU(cudaMemsetAsync(c->d_images, 0, c->images_bytes, c->stream));
-    CU(cudaMalloc(&c->d_flags, (size_t)n_groups * (size_t)c->flag_elems * sizeof(unsigned)));
-    CU(cudaMemsetAsync(c->d_flags, 0, (size_t)n_groups * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
-    c->launch_seq = 0;
-    c->ctrl_bytes = 256 + (size_t)n_groups * sizeof(GroupWs);
-    CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
-    CU(cudaMalloc(&c->d_partials, (size_t)n_groups * G * BF_NSUMS * sizeof(double)));
+static int configure(bf_ctx *c, int n_slices) {
+    const int want = max_groups(c);
+    if (want != c->n_groups_alloc || !c->d_images) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->d_images) cudaFree(c->d_images);
+        if (c->d_ctrl) cudaFree(c->d_ctrl);
+        if (c->d_partials) cudaFree(c->d_partials);
+        if (c->d_flags) cudaFree(c->d_flags);
+        c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr; c->d_flags = nullptr;
+        c->n_groups_alloc = want;
+        c->images_bytes = (size_t)want * 2 * (size_t)c->img_elems * sizeof(u64);
+        CU(cudaMalloc(&c->d_images, c->images_bytes));
+        CU(cudaMemsetAsync(c->d_images, 0, c->images_bytes, c->stream));
+        CU(cudaMalloc(&c->d_flags, (size_t)want * (size_t)c->flag_elems * sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)want * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+        c->launch_seq = 0;
+        c->ctrl_bytes = 256 + (size_t)want * sizeof(GroupWs);
+        CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
+        // one partial record per CTA slot, whatever the grouping
+        CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 2 * BF_NSUMS * sizeof(double)));
+    }
+    pick_launch(c, n_slices, &c->G, &c->n_groups);
     return BF_OK;
 }
 
@@ -490,7 +546,8 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaMalloc(&c->d_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMalloc(slices)", e);
     if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
 
-    if ((e = cudaFuncSetAttribute(bf_minimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
@@ -504,7 +561,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
     cudaFree(c->d_events); cudaFree(c->d_pr); cudaFree(c->d_nxy); cudaFree(c->d_slices);
     cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
-    cudaFree(c->d_stage);
+    cudaFree(c->d_stage); cudaFree(c->d_prof);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -516,19 +573,24 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     if (!strcmp(key, "group_size")) c->opt_group = (int)value;
     else if (!strcmp(key, "iter_cap")) c->iter_cap = (int)std::max(1LL, value);
     else if (!strcmp(key, "min_events")) c->min_events = (int)value;
-    else if (!strcmp(key, "l2_budget_mb")) c->l2_budget_mb = std::max(1LL, value);
+    else if (!strcmp(key, "min_group")) c->min_group = (int)std::max(1LL, value);
+    else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
+    else if (!strcmp(key, "profile")) c->profile = (int)value;
+    else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = value >= 2 ? 2 : 1;
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
     return BF_OK;
 }
 
 long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!c || !key) return -1;
-    if (!strcmp(key, "group_size")) return c->G ? c->G : pick_group(c);
-    if (!strcmp(key, "n_groups")) return c->n_groups ? c->n_groups : std::max(1, c->sms / pick_group(c));
+    if (!strcmp(key, "group_size")) return c->G;          // of the last launch
+    if (!strcmp(key, "n_groups")) return c->n_groups;
+    if (!strcmp(key, "min_group")) return c->min_group;
+    if (!strcmp(key, "image_budget_mb")) return c->image_budget_mb;
     if (!strcmp(key, "iter_cap")) return c->iter_cap;
     if (!strcmp(key, "min_events")) return c->min_events;
-    if (!strcmp(key, "l2_budget_mb")) return c->l2_budget_mb;
     if (!strcmp(key, "sms")) return c->sms;
+    if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;
     if (!strcmp(key, "image_bytes")) return c->img_elems * 8;
     if (!strcmp(key, "smem_bytes")) return (long long)smem_bytes();
     return -1;
@@ -542,6 +604,16 @@ int bf_ctx_set_stream(bf_ctx *c, void *cuda_stream) {
     CU(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return BF_OK;
+}
+
+// Debug: copies the per-CTA phase cycle counters of the last profiled launch ("profile" option)
+// into out[ctas][16]; returns the number of CTAs.
+int bf_debug_profile(bf_ctx *c, long long *out, int max_ctas) {
+    if (!c || !out || !c->d_prof) return fail(BF_ERR_STATE, "profiling was not enabled");
+    const int n = std::min(std::min(max_ctas, 1024), c->n_groups * c->G);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->d_prof, (size_t)n * BF_NPROF * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int bf_batch_results_device(bf_ctx *c, void **dev_ptr, long long *bytes) {
@@ -633,7 +705,7 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
     if (!c->uploaded) return fail(BF_ERR_STATE, "bf_batch_launch before bf_batch_upload");
     CU(cudaSetDevice(c->device));
     if (c->n_slices == 0) { c->ran = true; return BF_OK; }
-    int rc = configure(c);
+    int rc = configure(c, c->n_slices);
     if (rc != BF_OK) return rc;
     if (want_events && !c->d_nxy) CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
     CU(cudaMemsetAsync(c->d_ctrl, 0, c->ctrl_bytes, c->stream));
@@ -647,9 +719,15 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
     if ((rc = next_tag_base(c, &P.tag_base)) != BF_OK) return rc;
     P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
+    P.prof = nullptr;
+    if (c->profile) {
+        if (!c->d_prof) CU(cudaMalloc(&c->d_prof, (size_t)1024 * BF_NPROF * sizeof(long long)));
+        CU(cudaMemsetAsync(c->d_prof, 0, (size_t)1024 * BF_NPROF * sizeof(long long), c->stream));
+        P.prof = c->d_prof;
+    }
     void *args[] = {&P};
-    CU(cudaLaunchCooperativeKernel((void *)bf_minimize_kernel, dim3(c->n_groups * c->G), dim3(BF_NT), args,
-                                   smem_bytes(), c->stream));
+    void *kern = c->ctas_per_sm == 2 ? (void *)bf_minimize_kernel<2> : (void *)bf_minimize_kernel<1>;
+    CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes(), c->stream));
     c->launches += 1;
     c->ran = true;
     c->have_events = want_events != 0;
@@ -753,7 +831,7 @@ static int stage_image(bf_ctx *c, int n, const double *pr_x, const double *pr_y,
     if (w < 0 || h < 0 || rows > c->max_scale * c->res_x || cols > c->max_scale * c->res_y)
         return fail(BF_ERR_ARG, "image %dx%d exceeds the context's capacity", rows, cols);
     CU(cudaSetDevice(c->device));
-    int rc = configure(c);
+    int rc = configure(c, 1);
     if (rc != BF_OK) return rc;
     const size_t P = (size_t)rows * cols;
     const int grid = c->sms;

@@ -25,6 +25,9 @@
 // ---- compile-time geometry -------------------------------------------------------------------
 #define BF_NT 512              // threads per CTA (16 warps)
 #define BF_NW (BF_NT / 32)
+#ifndef BF_MIN_CTAS
+#define BF_MIN_CTAS 1          // resident CTAs per SM the minimise kernel is compiled for (register cap = 65536 / (BF_NT * this))
+#endif
 #define BF_BORDER 4            // zero border of the stored image (>= scale/2 + 1)
 #define BF_CELL_ROWS 8         // output rows per cell
 #define BF_LIST_CAP 4096       // active-cell list entries per scan chunk
@@ -82,7 +85,11 @@ struct KParams {
     int min_events;          // 1000 (optimizer_rolling.h:57)
     int iter_cap;
     int want_events;
+    long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
 };
+#define BF_NPROF 16
+enum { PF_EVENT = 0, PF_BAR_A, PF_SCAN, PF_CELLS, PF_REDUCE, PF_BAR_B, PF_SERIAL, PF_PROLOGUE, PF_FINAL, PF_ITERS, PF_SLICES,
+       PF_BAR_A_SPIN, PF_BAR_B_SPIN, PF_TOTAL };
 
 // ---- small PTX helpers ------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -90,6 +97,12 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -101,15 +114,25 @@ __device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {
 
 // Barrier over the G CTAs of one group (all co-resident: cooperative launch).  `target` is the
 // CTA-local running arrival total; the counter is zeroed by the host before every launch.
-__device__ __forceinline__ void group_barrier(unsigned *counter, unsigned &target, int G) {
+__device__ __forceinline__ long long group_barrier(unsigned *counter, unsigned &target, int G) {
     __syncthreads();
     target += (unsigned)G;
+    long long spin = 0;
     if (threadIdx.x == 0) {
+        const long long t0 = clock64();
         red_release_add_u32(counter, 1u);
-        while (ld_acquire_u32(counter) < target) {
+        // Poll with a RELAXED (L2) load and NO acquire fence.  An ld.acquire / fence.acq_rel.gpu here
+        // compiles to CCTL.IVALL -- a full L1 invalidation that the next load of the SM waits ~20k
+        // cycles for (measured) -- and it buys nothing: every cross-CTA read in this kernel (cell flags,
+        // image patches, partial sums, bbox, slice id) is an L2-coherent ld.cg / relaxed.gpu load, the
+        // producers drained their writes with MEMBAR.GPU before arriving (red.release), and the other
+        // threads of this CTA are ordered behind this poll by the bar.sync below.
+        while (ld_relaxed_u32(counter) < target) {
         }
+        spin = clock64() - t0;
     }
     __syncthreads();
+    return spin;   // cycles thread 0 spent between its arrival and the release (valid in thread 0)
 }
 
 // ---- exact division by the two constants of Event::apply_project (event.h:164-168) ----------
@@ -304,6 +327,7 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
     float A[C::AR];
 #pragma unroll
     for (int r = 0; r < C::AR; ++r) {
+        __syncwarp();   // reconverge after the previous row's data-dependent unpack branch (see group_sums)
         u64 v = 0;
 #pragma unroll
         for (int d = 0; d <= 2 * SH; ++d) v += P[r + d];      // patch rows r .. r+2SH  <->  image rows centred on A row r
@@ -319,10 +343,12 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
     // (outputs are lanes H..31-H) nor neighbours of outputs (lanes H-1..32-H need lanes 0..31 only).
     const bool out_lane = (lane >= C::H) && (lane < 32 - C::H);
     const int j = cj * C::CW + lane - C::H;
+    __syncwarp();
     float L0 = __shfl_up_sync(0xffffffffu, A[0], 1), R0 = __shfl_down_sync(0xffffffffu, A[0], 1);
     float L1 = __shfl_up_sync(0xffffffffu, A[1], 1), R1 = __shfl_down_sync(0xffffffffu, A[1], 1);
 #pragma unroll
     for (int r = 1; r <= BF_CELL_ROWS; ++r) {
+        __syncwarp();   // the occupancy / validity branches below diverge per lane
         const float L2 = __shfl_up_sync(0xffffffffu, A[r + 1], 1), R2 = __shfl_down_sync(0xffffffffu, A[r + 1], 1);
         const int i = ci * BF_CELL_ROWS + r - 1;
         const float v = A[r];
@@ -381,6 +407,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ void acc_block_reduce(const Acc &a, double *sred /* [BF_NW][BF_NSUMS] */, double *slot) {
     double v[BF_NSUMS] = {(double)a.cnt, (double)a.si, (double)a.sj, a.sgx, a.sgy, a.sigx, a.sjgx, a.sigy, a.sjgy};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < BF_NSUMS; ++k) {
         v[k] = warp_sum(v[k]);
@@ -418,6 +445,7 @@ __device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g,
             if (c < n_cells && __ldcg(flags + c) == tag) { live |= 1u << k; ++mine; }
         }
         int incl = mine;
+        __syncwarp();
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int nb = __shfl_up_sync(0xffffffffu, incl, o);
@@ -445,17 +473,123 @@ __device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g,
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):
 // every CTA of the group obtains the bit-identical result.  Call from warp 0; result valid in all lanes.
-__device__ __forceinline__ void group_sums(BfSums &s, const double *partials, int G) {
+__device__ __forceinline__ void group_sums(BfSums &s, const double *partials, int G, long long *dbg = nullptr) {
     const int lane = threadIdx.x & 31;
     double v[BF_NSUMS];
 #pragma unroll
     for (int k = 0; k < BF_NSUMS; ++k) v[k] = 0.0;
+    const long long t0 = dbg ? clock64() : 0;
     for (int r = lane; r < G; r += 32) {
 #pragma unroll
         for (int k = 0; k < BF_NSUMS; ++k) v[k] += __ldcg(partials + r * BF_NSUMS + k);
     }
+    if (dbg) {
+        double z = 0;
+#pragma unroll
+        for (int k = 0; k < BF_NSUMS; ++k) z += v[k];
+        if (z == -1.2345) v[0] = 0;
+        if (lane == 0) dbg[0] += clock64() - t0;
+    }
+    // The lane-strided loop diverges.  Without an explicit reconvergence point the shuffles below run
+    // through the compiler's divergent-warp fallback (BRA.DIV handlers): measured 23.8k vs 1.9k cycles.
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < BF_NSUMS; ++k) v[k] = warp_sum(v[k]);
     s.cnt = v[0]; s.si = v[1]; s.sj = v[2]; s.sgx = v[3]; s.sgy = v[4];
     s.sigx = v[5]; s.sjgx = v[6]; s.sigy = v[7]; s.sjgy = v[8];
+}
+
+// sin/cos of the accumulated rotation.  |crl| is ~1e-4 rad in practice: a degree-11/10 Taylor
+// polynomial is accurate to < 1 ulp for |x| <= 2^-5 and costs ~20 dependent fp64 operations instead
+// of the ~200 of the generic sincos; larger angles take the library path.
+__device__ __forceinline__ void sincos_small(double x, double &s, double &c) {
+    if (fabs(x) <= 0.03125) {
+        const double z = x * x;
+        double ps = 1.0 / 39916800.0;
+        ps = ps * z - 1.0 / 362880.0;   // -fmad=false keeps these as separate mul/add; accuracy is ample
+        ps = ps * z + 1.0 / 5040.0;
+        ps = ps * z - 1.0 / 120.0;
+        ps = ps * z + 1.0 / 6.0;
+        s = x - x * z * ps;
+        double pc = 1.0 / 3628800.0;
+        pc = pc * z - 1.0 / 40320.0;
+        pc = pc * z + 1.0 / 720.0;
+        pc = pc * z - 1.0 / 24.0;
+        pc = pc * z + 0.5;
+        c = 1.0 - z * pc;
+    } else {
+        sincos(x, &s, &c);
+    }
+}
+
+// Warp-cooperative form of bf_opt_advance (bf_logic.h): identical arithmetic, but the independent
+// IEEE fp64 divides run on different lanes (lane & 3 selects dx / dy / rot / div, lane & 1 the
+// centre coordinate), which cuts the dependent chain from ~16 divides to 3.  Call from warp 0 with
+// `s` identical in all lanes; o and next live in shared memory.  Returns the continue flag (all lanes).
+__device__ __forceinline__ bool opt_advance_warp(BfOpt &o, const BfGeom &g, const BfSums &s, int i0, int j0,
+                                                 int max_iter, int iter_cap, BfProj &next) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int p = lane & 3;
+    const double cnt = s.cnt;
+    // centre of mass (object_model.cpp:122-125): even lanes cx, odd lanes cy
+    const double c_img = ((lane & 1) ? s.sj : s.si) / cnt;
+    __syncwarp();
+    const double cx_img = __shfl_sync(FULL, c_img, 0), cy_img = __shfl_sync(FULL, c_img, 1);
+    const double ox = cx_img - (double)i0, oy = cy_img - (double)j0;
+    // mean gradient / rotation / divergence (object_model.cpp:35-38), see bf_sums_to_model
+    double num;
+    if (p == 0) num = s.sgx;
+    else if (p == 1) num = s.sgy;
+    else if (p == 2) { num = s.sigy - s.sjgx; num = num - ox * s.sgy; num = num + oy * s.sgx; }
+    else { num = s.sigx + s.sjgy; num = num - ox * s.sgx; num = num - oy * s.sgy; }
+    const double val = num / cnt;
+    // update_accumulators (object_model.h:48-53)
+    float dvd = p == 0 ? o.x_div : p == 1 ? o.y_div : p == 2 ? o.rot_div : o.div_div;
+    double tot = p == 0 ? o.m.total_dx : p == 1 ? o.m.total_dy : p == 2 ? o.m.total_rot : o.m.total_div;
+    const float old = p == 0 ? o.old_dx : p == 1 ? o.old_dy : p == 2 ? o.old_rot : o.old_div;
+    const double qa = val / (double)dvd;
+    tot += qa;
+    // centre back to sensor units (optimizer_rolling.h:330-331)
+    const double cen = (c_img - ((lane & 1) ? g.y_shift : g.x_shift)) / (double)g.scale;
+    __syncwarp();   // the per-lane selects above may have been compiled as branches
+    const double cx = __shfl_sync(FULL, cen, 0), cy = __shfl_sync(FULL, cen, 1);
+    const double tdx = __shfl_sync(FULL, tot, 0), tdy = __shfl_sync(FULL, tot, 1);
+    const double trot = __shfl_sync(FULL, tot, 2), tdiv = __shfl_sync(FULL, tot, 3);
+    const int iters = o.iters + 1;
+
+    bool stop = false;
+    int rc = o.rc;
+    bool flip = false;
+    if (!(cnt > 0)) { rc = BF_RC_DEGENERATE; stop = true; }
+    if (!stop && iters > 1) {
+        if (max_iter > 0 && iters > max_iter) stop = true;           // :94-96
+        else { flip = (val * (double)old < 0); if (flip) dvd *= 2; } // :98-101
+    }
+    const float lim = p < 2 ? 320.0f : 32000.0f;                     // :76-79
+    const double th = p < 2 ? 1e-5 : (p == 2 ? 1e-4 : 1e-1);         // :81-84
+    // val / (2 d) == (val / d) / 2 exactly (power-of-two scaling), so the doubled divider needs no new divide
+    const double cq = flip ? qa * 0.5 : qa;
+    __syncwarp();
+    const bool any_below = (__ballot_sync(FULL, dvd < lim) & 0xfu) != 0u;
+    const bool all_conv = (__ballot_sync(FULL, fabs(cq) < th) & 0xfu) == 0xfu;
+    if (!stop) {
+        if (!any_below) stop = true;
+        else if (all_conv) stop = true;
+        else if (iters >= iter_cap) { rc = BF_RC_ITER_CAP; stop = true; }
+    }
+    double sn, cs;
+    sincos_small(-trot, sn, cs);
+    if (lane < 4) {
+        if (p == 0) { o.m.dx = val; o.m.total_dx = tot; o.x_div = dvd; if (!stop) o.old_dx = (float)val; }
+        else if (p == 1) { o.m.dy = val; o.m.total_dy = tot; o.y_div = dvd; if (!stop) o.old_dy = (float)val; }
+        else if (p == 2) { o.m.rot = val; o.m.total_rot = tot; o.rot_div = dvd; if (!stop) o.old_rot = (float)val; }
+        else { o.m.div = val; o.m.total_div = tot; o.div_div = dvd; if (!stop) o.old_div = (float)val; }
+    }
+    if (lane == 0) {
+        o.m.cx = cx; o.m.cy = cy; o.m.cnt = (uint32_t)cnt;
+        o.iters = iters; o.rc = rc;
+        next.dnx = -tdx; next.dny = -tdy; next.cx = cx; next.cy = cy; next.div = tdiv; next.c = cs; next.s = sn;
+    }
+    return !stop;
 }

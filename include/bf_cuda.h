@@ -150,6 +150,10 @@ long long bf_ctx_launch_count(bf_ctx *ctx);
  * the per-slice flow) without a host round trip. */
 int bf_batch_results_device(bf_ctx *ctx, void **dev_ptr, long long *bytes);
 
+/* Debug aid: with option "profile" = 1 the minimise kernel accumulates clock64 cycles per phase and
+ * per CTA; this copies them out as out[ctas][16] (see PF_* in csrc/bf_device.cuh). */
+int bf_debug_profile(bf_ctx *ctx, long long *out, int max_ctas);
+
 int bf_batch_size(bf_ctx *ctx);
 int bf_batch_result(bf_ctx *ctx, int slot, bf_slice_result *out);
 /* Replaces AccelLib::writeout_events (accel_lib.h:310-329): per-event state after run().
