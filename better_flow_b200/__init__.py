@@ -57,7 +57,7 @@ ABI_SYMBOLS = (
     "bf_batch_staging", "bf_batch_add_staged", "bf_batch_upload", "bf_batch_launch", "bf_batch_download",
     "bf_batch_sync", "bf_batch_run", "bf_batch_time_launches", "bf_ctx_launch_count", "bf_batch_size",
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
-    "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile",
+    "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile", "bf_model_from_image",
 )
 
 _lib = None
@@ -295,6 +295,15 @@ class Context:
         gy = np.zeros((w + scale, h + scale), dtype=np.float32) if want_grad else None
         self._chk(self.lib.bf_fast_model(self.h, len(px), _ptr(px), _ptr(py), _ptr(t), _ptr(nz), w, h, scale,
                                          int(x_sh), int(y_sh), _ptr(out7), _ptr(gx), _ptr(gy)))
+        return (out7, gx, gy) if want_grad else out7
+
+    def model_from_image(self, img, want_grad=False):
+        im = np.ascontiguousarray(img, dtype=np.float32)
+        out7 = np.zeros(7)
+        gx = np.zeros_like(im) if want_grad else None
+        gy = np.zeros_like(im) if want_grad else None
+        self.lib.bf_model_from_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._chk(self.lib.bf_model_from_image(self.h, im.shape[0], im.shape[1], _ptr(im), _ptr(out7), _ptr(gx), _ptr(gy)))
         return (out7, gx, gy) if want_grad else out7
 
     def project(self, fr_x, fr_y, t_ns, pr_x, pr_y, dnx, dny, cx, cy, div, crl):

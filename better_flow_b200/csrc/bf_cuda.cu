@@ -307,6 +307,66 @@ __global__ void bf_stage_finish_kernel(const StageParams P, int G) {
     }
 }
 
+// ObjectModel::update / AccelLib::Sobel_cpu on a dense f32 image handed in by the caller (debug and
+// API-completeness path; the optimiser itself never materialises this image).  One thread per pixel,
+// taps straight from global memory (L1/L2 absorb the 9x reuse).
+__global__ void __launch_bounds__(256) bf_dense_model_kernel(int rows, int cols, const float *img, float *gx_out,
+                                                             float *gy_out, double *partials) {
+    __shared__ double sred[8 * BF_NSUMS];
+    Acc acc;
+    acc_zero(acc);
+    const int i0 = rows / 2, j0 = cols / 2;
+    const long long P = (long long)rows * cols;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / cols), j = (int)(k - (long long)i * cols);
+        const float v = img[k];
+        float gx = 0.0f, gy = 0.0f;
+        if (BF_OCC(v)) {
+            acc.cnt += 1; acc.si += i; acc.sj += j;
+            if (i >= 1 && i < rows - 1 && j >= 1 && j < cols - 1) {
+                const float *c = img + k;
+                const float L0 = c[-cols - 1], L1 = c[-1], L2 = c[cols - 1];
+                const float U = c[-cols], D = c[cols];
+                const float R0 = c[-cols + 1], R1 = c[1], R2 = c[cols + 1];
+                if (BF_OCC(L0) && BF_OCC(L1) && BF_OCC(L2) && BF_OCC(U) && BF_OCC(D) && BF_OCC(R0) && BF_OCC(R1) && BF_OCC(R2)) {
+                    float a = __fmul_rn(L0, 3.0f);
+                    a = __fadd_rn(a, __fmul_rn(L2, -3.0f));
+                    a = __fadd_rn(a, __fmul_rn(U, 10.0f));
+                    a = __fadd_rn(a, __fmul_rn(D, -10.0f));
+                    a = __fadd_rn(a, __fmul_rn(R0, 3.0f));
+                    a = __fadd_rn(a, __fmul_rn(R2, -3.0f));
+                    float b = __fmul_rn(L0, 3.0f);
+                    b = __fadd_rn(b, __fmul_rn(L1, 10.0f));
+                    b = __fadd_rn(b, __fmul_rn(L2, 3.0f));
+                    b = __fadd_rn(b, __fmul_rn(R0, -3.0f));
+                    b = __fadd_rn(b, __fmul_rn(R1, -10.0f));
+                    b = __fadd_rn(b, __fmul_rn(R2, -3.0f));
+                    gx = a; gy = b;
+                    const double di = (double)(i - i0), dj = (double)(j - j0), dgx = (double)gx, dgy = (double)gy;
+                    acc.sgx += dgx; acc.sgy += dgy;
+                    acc.sigx += di * dgx; acc.sjgx += dj * dgx; acc.sigy += di * dgy; acc.sjgy += dj * dgy;
+                }
+            }
+        }
+        if (gx_out) gx_out[k] = gx;
+        if (gy_out) gy_out[k] = gy;
+    }
+    double v[BF_NSUMS] = {(double)acc.cnt, (double)acc.si, (double)acc.sj, acc.sgx, acc.sgy, acc.sigx, acc.sjgx, acc.sigy, acc.sjgy};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) sred[warp * BF_NSUMS + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < BF_NSUMS) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += sred[w * BF_NSUMS + threadIdx.x];
+        partials[blockIdx.x * BF_NSUMS + threadIdx.x] = s;
+    }
+}
+
 // AccelLib::project_4param_reinit (accel_lib.h:263-267)
 __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const unsigned short *fr_y,
                                         const int *t, double *pr_x, double *pr_y, double *nx, double *ny,
@@ -907,6 +967,37 @@ int bf_fast_model(bf_ctx *c, int n, const double *pr_x, const double *pr_y, cons
                   int w, int h, int scale, int x_sh, int y_sh, double *out7, float *gx, float *gy) {
     if (!out7) return fail(BF_ERR_ARG, "bf_fast_model: null output");
     return stage_image(c, n, pr_x, pr_y, t_ns, noise, w, h, scale, x_sh, y_sh, nullptr, out7, gx, gy);
+}
+
+int bf_model_from_image(bf_ctx *c, int rows, int cols, const float *img, double *out7, float *gx, float *gy) {
+    if (!c || rows <= 0 || cols <= 0 || !img) return fail(BF_ERR_ARG, "bf_model_from_image: bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = configure(c, 1);
+    if (rc != BF_OK) return rc;
+    const size_t P = (size_t)rows * cols;
+    const int grid = c->sms;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_img = take(P * 4), o_gx = take(P * 4), o_gy = take(P * 4);
+    const size_t o_part = take((size_t)grid * BF_NSUMS * 8), o_out7 = take(64);
+    if ((rc = stage_alloc(c, off)) != BF_OK) return rc;
+    unsigned char *base = (unsigned char *)c->d_stage;
+    CU(cudaMemcpyAsync(base + o_img, img, P * 4, cudaMemcpyHostToDevice, c->stream));
+    bf_dense_model_kernel<<<grid, 256, 0, c->stream>>>(rows, cols, (const float *)(base + o_img), gx ? (float *)(base + o_gx) : nullptr,
+                                                       gy ? (float *)(base + o_gy) : nullptr, (double *)(base + o_part));
+    StageParams S;
+    memset(&S, 0, sizeof S);
+    S.g.rows = rows; S.g.cols = cols;
+    S.partials = (double *)(base + o_part);
+    S.out7 = (double *)(base + o_out7);
+    bf_stage_finish_kernel<<<1, 32, 0, c->stream>>>(S, grid);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    if (gx) CU(cudaMemcpyAsync(gx, base + o_gx, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (gy) CU(cudaMemcpyAsync(gy, base + o_gy, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out7) CU(cudaMemcpyAsync(out7, S.out7, 7 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
 }
 
 int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, double *pr_x,

@@ -1,0 +1,293 @@
+// better_flow/dvs_flow.h -- slice manager (reference: better_flow_core/include/better_flow/dvs_flow.h).
+// Same class template, constructor and public methods: events are pushed one by one, a slice is
+// (re)computed when enough new events or enough time have accumulated, the model of the previous
+// slice warm-starts the next one unless stm is disabled.
+//
+// Additions over the reference, all opt-in:
+//   * run-time buffer capacity / time span (the template arguments stay the defaults),
+//   * set_batch(n): with stm disabled slices are independent, so n of them are queued and minimised
+//     by ONE persistent-kernel launch (bf_batch_*),
+//   * set_flow_out(stream): one machine-readable line per slice,
+//   * set_quiet(): suppress the reference's per-slice dump of every past model.
+// Video / picture generation and the interactive mode are GUI features and are accepted but ignored.
+#ifndef BF_DVS_FLOW_H
+#define BF_DVS_FLOW_H
+
+#include <map>
+
+#include <better_flow/common.h>
+#include <better_flow/event.h>
+#include <better_flow/event_file.h>
+#include <better_flow/optimizer_rolling.h>
+
+template <size_t MAX_SZ, sll SPAN> class DVS_flow {
+public:
+    // Buffer for incoming events (aka 'slice')
+    CircularArray<Event, MAX_SZ, SPAN> ev_buffer;
+
+protected:
+    ull on_ev_change, on_time_change;        // triggers
+    sll time_diff, event_diff;               // time passed / new events since the last slice
+    ull last_slice_time, current_slice_time;
+    ObjectModel last_model;                  // starting point of the next minimisation
+    bool accumulate;
+    std::vector<LinearEventCloudTemplate<Event>> accumulated;
+    bool manual_mode;
+    int max_iter;
+    int scale;
+    bool stm_disable;
+
+    struct SliceLog {                        // what the reference prints per remembered slice (:245-252)
+        ObjectModel model;
+        size_t size;
+        ull ts_first, ts_last;
+    };
+    std::vector<SliceLog> motion_memory;
+
+    struct Pending {                         // a slice queued for a batched launch
+        std::vector<bf_event> packed;
+        SliceLog log;
+        LinearEventCloudTemplate<Event> copy; // only when accumulating
+        ull slice_start;
+    };
+    std::vector<Pending> pending_;
+    int batch_;
+    bool quiet_;
+    std::ostream *flow_out_;
+    ull slices_done_;
+    ull events_done_;
+    ull iters_done_;
+
+public:
+    DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time = 0)
+        : on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
+          last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
+          scale(3), stm_disable(false), batch_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          iters_done_(0) {}
+
+    // run-time sized variant (CLI flags --max-events / --slice-time)
+    DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time, size_t capacity, sll span)
+        : ev_buffer(capacity, span), on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
+          last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
+          scale(3), stm_disable(false), batch_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          iters_done_(0) {}
+
+    ~DVS_flow() {}
+
+    bool add_event(Event &ev);
+    void recompute();
+    void flush();   // minimise whatever is still queued (batch mode)
+
+    void set_accumulate(bool val = true) { accumulate = val; }
+    LinearEventCloudTemplate<Event> get_accumulated();
+    void set_manual_mode(bool val = true) {
+        manual_mode = val;
+        if (val) std::cerr << "interactive mode is a GUI feature of the reference and is ignored" << std::endl;
+    }
+    void set_max_iter(int val = -1) { max_iter = val; }
+    void set_scale(int val = 3) { scale = val; }
+    void set_generate_video(bool val = true, std::string = "out.avi", int = 30) {
+        if (val) std::cerr << "video output is a visualisation feature of the reference and is ignored" << std::endl;
+    }
+    void set_generate_pictures(bool val = true, std::string = "./") {
+        if (val) std::cerr << "picture output is a visualisation feature of the reference and is ignored" << std::endl;
+    }
+    void set_stm_disable(bool val = true) { stm_disable = val; }
+
+    sll get_buf_size() { return ev_buffer.size(); }
+    sll get_time_diff() { return time_diff; }
+    sll get_buf_time_diff() { return current_slice_time - slice_start_time(); }
+
+    // extensions
+    void set_batch(int n) { batch_ = n < 1 ? 1 : n; }
+    void set_quiet(bool q = true) { quiet_ = q; }
+    void set_flow_out(std::ostream *os) { flow_out_ = os; }
+    ObjectModel get_last_model() { return last_model; }
+    ull slices_done() const { return slices_done_; }
+    ull events_done() const { return events_done_; }
+    ull iterations_done() const { return iters_done_; }
+
+protected:
+    // dvs_flow.h:186-193: the oldest timestamp when the buffer overflowed, else now - SPAN
+    ull slice_start_time() {
+        if (ev_buffer.size() == ev_buffer.capacity()) return ev_buffer[ev_buffer.capacity() - 1].timestamp;
+        const ull span = (ull)ev_buffer.span();
+        return (current_slice_time > span) ? current_slice_time - span : 0;
+    }
+
+    void log_slice(const SliceLog &l, int iters, int rc) {
+        motion_memory.push_back(l);
+        last_model = l.model;
+        slices_done_ += 1;
+        events_done_ += l.size;
+        iters_done_ += (ull)iters;
+        if (!quiet_) {
+            // the reference dumps every remembered slice after each recompute (dvs_flow.h:245-252)
+            std::cout << "\n\n------------------------\n";
+            for (auto &s : motion_memory) {
+                std::cout << s.model << "\n";
+                std::cout << s.size << "\t" << s.ts_first << "\t" << s.ts_last << "\n";
+            }
+        }
+        if (flow_out_) {
+            std::ostream &o = *flow_out_;
+            const auto old = o.precision(17);
+            o << (slices_done_ - 1) << " " << l.size << " " << iters << " " << rc << " " << l.model.total_dx << " " << l.model.total_dy
+              << " " << l.model.total_rot << " " << l.model.total_div << " " << l.model.cx << " " << l.model.cy << " " << l.model.dx
+              << " " << l.model.dy << " " << l.model.rot << " " << l.model.div << " " << l.model.cnt << "\n";
+            o.precision(old);
+        }
+    }
+
+    void run_pending();
+};
+
+template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::add_event(Event &ev) {
+    ev_buffer.push_back(ev);
+    event_diff++;
+    current_slice_time = ev.timestamp;
+    time_diff = current_slice_time - last_slice_time;   // time only increases
+    if ((event_diff < (sll)on_ev_change) && (time_diff < (sll)on_time_change)) return false;
+    recompute();
+    return true;
+}
+
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
+    const ull start = slice_start_time();
+
+    LinearEventPtrs e_ptrs;
+    e_ptrs.reserve(ev_buffer.size());
+    for (auto &e : ev_buffer) e_ptrs.push_back(&e);   // newest -> oldest (and SZ-1 elements when full)
+
+    SliceLog log;
+    log.size = e_ptrs.size();
+    log.ts_first = log.size ? e_ptrs[0].timestamp : 0;
+    log.ts_last = log.size ? e_ptrs[log.size - 1].timestamp : 0;
+
+    if (batch_ > 1 && stm_disable) {
+        // independent slice: snapshot it and minimise later together with its neighbours
+        Pending p;
+        p.slice_start = start;
+        p.packed.reserve(log.size);
+        for (auto &e : e_ptrs) {
+            e.reset();
+            e.set_local_time(start);
+            if (e.t > INT32_MAX || e.t < INT32_MIN) {
+                std::cerr << "DVS_flow: local time of an event exceeds +-2.1 s; shorten the slice" << std::endl;
+                std::exit(1);
+            }
+            bf_event b;
+            b.fr_x = (uint16_t)e.fr_x;
+            b.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u));
+            b.t_ns = (int32_t)e.t;
+            p.packed.push_back(b);
+        }
+        p.log = log;
+        if (accumulate)
+            for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) p.copy.push_back(ev_buffer[i]);
+        pending_.push_back(std::move(p));
+        if ((int)pending_.size() >= batch_) run_pending();
+    } else {
+        OptimizerRolling<LinearEventPtrs> optimizer;
+        optimizer.set_cloud(&e_ptrs, scale);
+        optimizer.set_time(start);
+        optimizer.set_maxiter(max_iter);
+        if (!stm_disable) optimizer.set_model(last_model);   // dvs_flow.h:218-219
+        const int rc = optimizer.run();
+        log.model = optimizer.get_model();
+        for (auto &e : ev_buffer) e.compute_uv();            // dvs_flow.h:234-235
+        log_slice(log, optimizer.iterations(), rc);
+        if (accumulate) {                                     // dvs_flow.h:341-346: oldest -> newest copy
+            LinearEventCloudTemplate<Event> cur;
+            for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);
+            accumulated.push_back(cur);
+        }
+    }
+    event_diff = 0;
+    last_slice_time = current_slice_time;
+}
+
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
+    if (pending_.empty()) return;
+    long long total = 0;
+    for (auto &p : pending_) total += (long long)p.packed.size();
+    bf_ctx *ctx = CudaDriver::context(total, (int)pending_.size(), scale);
+    auto check = [](int rc, const char *what) {
+        if (rc < 0) {
+            std::cerr << what << " failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+    };
+    check(bf_batch_reset(ctx), "bf_batch_reset");
+    for (auto &p : pending_) check(bf_batch_add_packed(ctx, p.packed.data(), (int)p.packed.size(), scale, max_iter, nullptr), "bf_batch_add_packed");
+    check(bf_batch_run(ctx, accumulate ? 1 : 0), "bf_batch_run");
+    std::vector<double> nx, ny, px, py;
+    for (size_t k = 0; k < pending_.size(); ++k) {
+        Pending &p = pending_[k];
+        bf_slice_result r;
+        check(bf_batch_result(ctx, (int)k, &r), "bf_batch_result");
+        p.log.model.from_pod(r.model);
+        log_slice(p.log, r.iters, r.rc);
+        if (accumulate) {
+            // the snapshot copy is oldest -> newest and includes the element the iterator skips when the
+            // buffer is full; the packed slice is newest -> oldest.  Map by walking backwards.
+            const size_t n = p.packed.size();
+            nx.resize(n); ny.resize(n); px.resize(n); py.resize(n);
+            check(bf_batch_events(ctx, (int)k, px.data(), py.data(), nx.data(), ny.data()), "bf_batch_events");
+            const size_t m = p.copy.size();
+            for (size_t i = 0; i < m; ++i) {
+                Event &e = p.copy[i];
+                const size_t from_newest = m - 1 - i;
+                if (from_newest < n) {
+                    e.pr_x = px[from_newest]; e.pr_y = py[from_newest]; e.nx = nx[from_newest]; e.ny = ny[from_newest];
+                    e.set_local_time(p.slice_start);
+                    if (r.flags & BF_FLAG_ALL_NOISE) e.noise = true;
+                    e.compute_uv();
+                    if (r.rc != BF_RC_SKIPPED) e.assume_score(0);
+                }
+            }
+            accumulated.push_back(p.copy);
+        }
+    }
+    pending_.clear();
+}
+
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::flush() { run_pending(); }
+
+// dvs_flow.h:350-389: concatenate the remembered slices, dropping from LATER slices every event that an
+// earlier slice already contains (same pixel, not newer, closer than 0.1 ms).  The reference does
+// this with nested linear scans; an index by pixel gives the same set in near-linear time.
+template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_SZ, SPAN>::get_accumulated() {
+    flush();
+    LinearEventCloudTemplate<Event> ret;
+    std::cout << "Aggregating events into one cloud...\n";
+    typedef std::map<std::pair<uint, uint>, std::vector<size_t>> PixelIndex;
+    std::vector<PixelIndex> index(accumulated.size());
+    for (size_t j = 0; j < accumulated.size(); ++j) {
+        auto &buf = accumulated[j];
+        for (size_t k = 0; k < buf.size(); ++k) index[j][std::make_pair(buf[k].fr_x, buf[k].fr_y)].push_back(k);
+    }
+    for (ull i = 0; i < accumulated.size(); ++i) {
+        std::cout << "\tBuffer: " << i << "\n";
+        auto &buf = accumulated[i];
+        for (auto &e : buf) {
+            if (e.t == -1) continue;
+            for (ull j = i + 1; j < accumulated.size(); ++j) {
+                auto it = index[j].find(std::make_pair(e.fr_x, e.fr_y));
+                if (it == index[j].end()) continue;
+                for (size_t k : it->second) {
+                    Event &o = accumulated[j][k];
+                    if (o - e > 0) continue;      // newer than e: the reference's scan has stopped by then
+                    if (o.t == -1) continue;
+                    if (e != o) continue;
+                    o.t = -1;
+                }
+            }
+            ret.push_back(e);
+        }
+    }
+    std::cout << "FInal buffer contains " << ret.size() << " events." << std::endl;
+    return ret;
+}
+
+#endif  // BF_DVS_FLOW_H

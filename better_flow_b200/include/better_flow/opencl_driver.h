@@ -1,0 +1,80 @@
+// better_flow/opencl_driver.h -- back-end selection.  The reference's OpenCLDriver is a static
+// singleton that picks an OpenCL device and JIT-builds gpu_impl.cl (reference:
+// better_flow_core/src/opencl_driver.cpp:14-60).  Here the same role is played by the CUDA library
+// behind include/bf_cuda.h; the class keeps its name and its two public members so that
+// `OpenCLDriver::init()` / `OpenCLDriver::enabled` in caller code keep compiling.
+// There is no CPU path: if no CUDA device can be opened, init() reports and exits, exactly as the
+// reference exits when its kernel file cannot be built (opencl_driver.cpp:43,50).
+#ifndef BF_OPENCL_DRIVER_H
+#define BF_OPENCL_DRIVER_H
+
+#include <better_flow/common.h>
+#include <bf_cuda.h>
+
+class CudaDriver {
+public:
+    static bool &enabled_ref() {
+        static bool e = false;
+        return e;
+    }
+    static int &device_ref() {
+        static int d = 0;
+        return d;
+    }
+
+    static void init(int device = 0) {
+        if (bf_cuda_init(device) != BF_OK) {
+            std::cerr << "CUDA back-end unavailable: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+        device_ref() = device;
+        enabled_ref() = true;
+    }
+
+    // One pooled context per process (the reference re-allocates device buffers for every slice,
+    // accel_lib.h:71-145 via dvs_flow.h:210).  Re-created only if a caller needs more capacity.
+    static bf_ctx *context(long long need_events, int need_slices, int need_scale) {
+        if (!enabled_ref()) init(device_ref());
+        State &s = state();
+        const bool fits = s.ctx && s.rows == RES_X && s.cols == RES_Y && need_events <= s.events &&
+                          need_slices <= s.slices && need_scale <= s.scale;
+        if (!fits) {
+            if (s.ctx) bf_ctx_destroy(s.ctx);
+            s.rows = RES_X; s.cols = RES_Y;
+            s.events = std::max<long long>(need_events + need_events / 4, 1 << 16);
+            s.slices = std::max(need_slices, 64);
+            s.scale = std::max(need_scale, s.scale);
+            s.ctx = bf_ctx_create(s.rows, s.cols, s.scale, s.events, s.slices);
+            if (!s.ctx) {
+                std::cerr << "bf_ctx_create failed: " << bf_last_error() << std::endl;
+                std::exit(1);
+            }
+        }
+        return s.ctx;
+    }
+
+    static void shutdown() {
+        State &s = state();
+        if (s.ctx) bf_ctx_destroy(s.ctx);
+        s.ctx = nullptr;
+    }
+
+private:
+    struct State {
+        bf_ctx *ctx = nullptr;
+        int rows = 0, cols = 0, slices = 0, scale = 3;
+        long long events = 0;
+    };
+    static State &state() {
+        static State s;
+        return s;
+    }
+};
+
+// Drop-in spelling used by the reference's callers (bf_motion_compensator.cpp:132-133, accel_lib.h:46).
+class OpenCLDriver : public CudaDriver {
+public:
+    static bool enabled_get() { return enabled_ref(); }
+};
+
+#endif  // BF_OPENCL_DRIVER_H

@@ -1,0 +1,75 @@
+"""Multi-GPU partition of the hot path.
+
+Time slices are independent once the warm start is disabled (reference --stm-disable semantics,
+dvs_flow.h:218-219), so the only multi-GPU structure is: cut the stream into slices, give every rank
+a block-cyclic share of them, minimise locally (no data-path collective), and gather the fixed-size
+per-slice result records once per batch.  One process per GPU; torch.distributed is plumbing only
+(NCCL on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+RECORD_F64 = 20   # slice id, rc, iters, n_events, flags, 11 model scalars, 4 dividers
+
+
+def partition(n_slices: int, world: int, rank: int, block: int = 4) -> list[int]:
+    """Block-cyclic assignment: blocks of `block` consecutive slices dealt round-robin to the ranks.
+    Consecutive slices of a stream have similar iteration counts, so dealing small blocks balances
+    the data-dependent GD lengths (26..924 steps in the survey) better than one contiguous chunk."""
+    out = []
+    for b0 in range(0, n_slices, block):
+        if (b0 // block) % world == rank:
+            out.extend(range(b0, min(n_slices, b0 + block)))
+    return out
+
+
+def pack_records(slice_ids, results) -> np.ndarray:
+    """Result dicts (better_flow_b200.Context.result) -> float64 records for the gather."""
+    rec = np.zeros((len(slice_ids), RECORD_F64), dtype=np.float64)
+    for k, (sid, r) in enumerate(zip(slice_ids, results)):
+        rec[k, 0] = sid
+        rec[k, 1] = r["rc"]
+        rec[k, 2] = r["iters"]
+        rec[k, 3] = r.get("n_events", 0)
+        rec[k, 4] = r.get("flags", 0)
+        rec[k, 5:16] = r["model"]
+        rec[k, 16:20] = r["dividers"]
+    return rec
+
+
+def unpack_record(row) -> dict:
+    return {"slice": int(row[0]), "rc": int(row[1]), "iters": int(row[2]), "n_events": int(row[3]),
+            "flags": int(row[4]), "model": np.array(row[5:16]), "dividers": np.array(row[16:20], dtype=np.float32)}
+
+
+def gather_records(local: np.ndarray, n_slices: int, dist=None, device="cpu") -> np.ndarray:
+    """All ranks' records in global slice order: ONE all_gather of equal-size buffers (ranks with fewer
+    slices pad with slice id -1)."""
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        order = np.argsort(local[:, 0], kind="stable")
+        return local[order]
+    world = dist.get_world_size()
+    cap = max(len(partition(n_slices, world, r)) for r in range(world))
+    buf = np.full((cap, RECORD_F64), -1.0)
+    buf[:len(local)] = local
+    mine = torch.from_numpy(buf).to(device)
+    out = torch.empty((world * cap, RECORD_F64), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    allrec = out.cpu().numpy()
+    allrec = allrec[allrec[:, 0] >= 0]
+    return allrec[np.argsort(allrec[:, 0], kind="stable")]
+
+
+def run_sharded(slices, minimise_batch, dist=None, device="cpu", block: int = 4):
+    """Minimise `slices` (the same global list on every rank) across the ranks of `dist`.
+
+    minimise_batch(list_of_slices) -> list of result dicts; on a GPU rank this is a
+    better_flow_b200.Context batch run, in the CPU tests it is the oracle.  Returns the records of
+    ALL slices in order, on every rank."""
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    ids = partition(len(slices), world, rank, block)
+    results = minimise_batch([slices[i] for i in ids]) if ids else []
+    return gather_records(pack_records(ids, results), len(slices), dist, device)

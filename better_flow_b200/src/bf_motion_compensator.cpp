@@ -1,0 +1,213 @@
+// bf_motion_compensator -- command-line front end, drop-in for the reference tool
+// (reference: better_flow_core/src/bf_motion_compensator.cpp).  Every flag of the reference is accepted
+// with the same meaning and the same stdout formats; the compile-time constants of the reference
+// (EVENT_WIDTH, TIME_WIDTH, RES_X/RES_Y, scale, max_iter) are additionally exposed as flags whose
+// defaults reproduce the reference.  The computation always runs on the CUDA back-end.
+#include <better_flow/common.h>
+#include <better_flow/dvs_flow.h>
+#include <better_flow/opencl_driver.h>
+
+#include <chrono>
+
+#define EVENT_WIDTH 50000
+#define TIME_WIDTH 0.2
+
+static float time_refresh = 0.033f;
+static unsigned long long int event_refresh = 20000;
+
+static bool manual = false;
+static bool quiet = false;
+static char *file = NULL;
+static char *outFileName = NULL;
+static bool gpu = false;
+static bool img = false;
+static bool video = false;
+static bool stm_disable = false;
+static bool bufferize_file = false;
+static std::string img_prefix = "./";
+static std::string video_name = "./out.avi";
+static int video_fps = 60;
+// additions
+static int max_iter = -1;
+static int scale = 3;
+static double slice_time = TIME_WIDTH;
+static long long max_events = EVENT_WIDTH;
+static int sensor_w = 240, sensor_h = 180;
+static char *flowOutName = NULL;
+static int batch = 1;
+static int device = 0;
+
+static void lPrintVersion() {
+    printf("DVS flow estimator (better flow), %s (build %s @ %s)\n", BF_VERSION, __DATE__, __TIME__);
+    printf("\tDefault maximum event memory of %i events\n\tand slice size of %f seconds (both run-time options here).\n",
+           EVENT_WIDTH, TIME_WIDTH);
+}
+
+static void usage(int ret) {
+    lPrintVersion();
+    printf("\nusage: bf_motion_compensator\n");
+    printf("    [--refresh-time={0.0 - inf}]\t\tRun processing when at least this amount of time (floatimg point,\n");
+    printf("                                \t\tseconds) has passed since the last processing, (default = %f)\n", time_refresh);
+    printf("    [--refresh-event-count={0 - inf}]\t\tRun processing when at least this number of new events has\n");
+    printf("                                     \t\tarrived since the last processing (default = %llu)\n", event_refresh);
+    printf("    [-i/--interactive]\tEnable interactive mode (ignored: GUI feature)\n");
+    printf("    [-G]\t\t\t\tUse GPU support (always on: the CUDA back-end is the only implementation)\n");
+    printf("    [--stm-disable]\t\t\t\tDo not use previous estimate as a starting point for a new estimate\n");
+    printf("    [--img]\t\t\t\tOutput flow images after every iteration (ignored: visualisation)\n");
+    printf("    [--img-prefix <name>]\t\t\t\tSpecify prefix for the generated image files (default = %s)\n", img_prefix.c_str());
+    printf("    [--video]\t\t\t\tOutput a video with flow frames (ignored: visualisation)\n");
+    printf("    [--video-name <name>]\t\t\t\tSpecify the name of the video file (default = %s)\n", video_name.c_str());
+    printf("    [--video-fps=<value>]\t\t\t\tSpecify video framerate (default = %i)\n", video_fps);
+    printf("    [--bufferize-file]\t\t\t\tRead input file to the buffer first (useful for performance testing)\n");
+    printf("    [--quiet]\t\t\t\tSuppress the per-slice model dump\n");
+    printf("    [-o <name>/--outfile=<name>]\tOutput filename (may be \"-\" for standard output)\n");
+    printf("    [--version]\t\t\t\tPrint better flow version\n");
+    printf("  additions (defaults reproduce the reference):\n");
+    printf("    [--max-iter=N]\t\t\tMaximum number of optimisation steps, -1 = until convergence (default = %i)\n", max_iter);
+    printf("    [--scale=N]\t\t\t\tImage scale 1/3/5 (default = %i)\n", scale);
+    printf("    [--slice-time=SEC]\t\t\tTime span of the event buffer (default = %f)\n", slice_time);
+    printf("    [--max-events=N]\t\t\tCapacity of the event buffer (default = %lld)\n", max_events);
+    printf("    [--sensor=WxH]\t\t\tSensor size in pixels (default = %ix%i)\n", sensor_w, sensor_h);
+    printf("    [--flow-out=<name>]\t\t\tWrite one line per slice: id n iters rc total_dx total_dy total_rot total_div cx cy dx dy rot div cnt\n");
+    printf("    [--batch=N]\t\t\t\tWith --stm-disable: minimise N slices per kernel launch (default = %i)\n", batch);
+    printf("    [--device=N]\t\t\tCUDA device (default = %i)\n", device);
+    printf("    <file to process or \"-\" for stdin>\n");
+    exit(ret);
+}
+
+int main(int argc, char *argv[]) {
+    if (argc == 1) usage(1);
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--help")) usage(0);
+        else if (!strcmp(argv[i], "-v") || !strcmp(argv[i], "--version")) { lPrintVersion(); return 0; }
+        else if (!strcmp(argv[i], "--quiet")) quiet = true;
+        else if (!strncmp(argv[i], "--refresh-time=", 15)) time_refresh = atof(argv[i] + 15);
+        else if (!strncmp(argv[i], "--refresh-event-count=", 22)) event_refresh = atoi(argv[i] + 22);
+        else if (!strcmp(argv[i], "-G")) gpu = true;
+        else if (!strcmp(argv[i], "-i") || !strcmp(argv[i], "--interactive")) manual = true;
+        else if (!strcmp(argv[i], "--bufferize-file")) bufferize_file = true;
+        else if (!strcmp(argv[i], "--stm-disable")) stm_disable = true;
+        else if (!strcmp(argv[i], "--img")) img = true;
+        else if (!strcmp(argv[i], "--img-prefix")) {
+            if (++i == argc) { fprintf(stderr, "No output file specified after --img-prefix option.\n"); usage(1); }
+            img_prefix = argv[i];
+        }
+        else if (!strcmp(argv[i], "--video")) video = true;
+        else if (!strcmp(argv[i], "--video-name")) {
+            if (++i == argc) { fprintf(stderr, "No output file specified after --video-name option.\n"); usage(1); }
+            video_name = argv[i];
+        }
+        else if (!strncmp(argv[i], "--video-fps=", 12)) video_fps = atoi(argv[i] + 12);
+        else if (!strcmp(argv[i], "-o")) {
+            if (++i == argc) { fprintf(stderr, "No output file specified after -o option.\n"); usage(1); }
+            outFileName = argv[i];
+        }
+        else if (!strncmp(argv[i], "--outfile=", 10)) outFileName = argv[i] + strlen("--outfile=");
+        else if (!strncmp(argv[i], "--max-iter=", 11)) max_iter = atoi(argv[i] + 11);
+        else if (!strncmp(argv[i], "--scale=", 8)) scale = atoi(argv[i] + 8);
+        else if (!strncmp(argv[i], "--slice-time=", 13)) slice_time = atof(argv[i] + 13);
+        else if (!strncmp(argv[i], "--max-events=", 13)) max_events = atoll(argv[i] + 13);
+        else if (!strncmp(argv[i], "--sensor=", 9)) {
+            if (sscanf(argv[i] + 9, "%dx%d", &sensor_w, &sensor_h) != 2) { fprintf(stderr, "Bad --sensor=WxH.\n"); usage(1); }
+        }
+        else if (!strncmp(argv[i], "--flow-out=", 11)) flowOutName = argv[i] + 11;
+        else if (!strncmp(argv[i], "--batch=", 8)) batch = atoi(argv[i] + 8);
+        else if (!strncmp(argv[i], "--device=", 9)) device = atoi(argv[i] + 9);
+        else if (!strcmp(argv[i], "-")) {}
+        else if (argv[i][0] == '-') { fprintf(stderr, "Unknown option \"%s\".\n", argv[i]); usage(1); }
+        else {
+            if (file != NULL) {
+                fprintf(stderr, "Multiple input files specified on command line: \"%s\" and \"%s\".\n", file, argv[i]);
+                usage(1);
+            }
+            else file = argv[i];
+        }
+    }
+    if (file == NULL) { fprintf(stderr, "No input file.\n"); usage(1); }
+    if (scale != 1 && scale != 3 && scale != 5) { fprintf(stderr, "--scale must be 1, 3 or 5.\n"); return 1; }
+    if (batch > 1 && !stm_disable) { fprintf(stderr, "--batch needs --stm-disable (warm-started slices form a chain).\n"); return 1; }
+    (void)gpu; (void)img; (void)video;
+
+    bf::set_sensor(sensor_h, sensor_w);   // RES_X = rows, RES_Y = columns
+    OpenCLDriver::init(device);           // same call site as the reference's -G branch (:132-133)
+
+    DVS_flow<EVENT_WIDTH, FROM_SEC(TIME_WIDTH)> estimator(event_refresh, FROM_SEC(time_refresh), 0, (size_t)max_events,
+                                                          (sll)FROM_SEC(slice_time));
+    if (outFileName != NULL) estimator.set_accumulate();
+    if (manual) estimator.set_manual_mode(true);
+    if (img) estimator.set_generate_pictures(true, img_prefix);
+    if (video) estimator.set_generate_video(true, video_name, video_fps);
+    if (stm_disable) estimator.set_stm_disable(true);
+    estimator.set_max_iter(max_iter);
+    estimator.set_scale(scale);
+    estimator.set_batch(batch);
+    estimator.set_quiet(quiet);
+    std::ofstream flow_out;
+    if (flowOutName != NULL) {
+        flow_out.open(flowOutName);
+        estimator.set_flow_out(&flow_out);
+    }
+
+    const auto wall0 = std::chrono::steady_clock::now();
+    const size_t flen = strlen(file);
+    const bool binary = flen > 4 && !strcmp(file + flen - 4, ".bin");
+    if (binary) bufferize_file = true;   // binary input is always read up front
+    if (bufferize_file) {
+        LinearEventCloud ec;
+        if (binary) EventFile::from_binary(&ec, file);
+        else EventFile::from_file(&ec, file);
+
+        clock_t begin = std::clock();
+        clock_t begin_slice = std::clock();
+        ull i = 0;
+        for (auto &e : ec) {
+            ++i;
+            bool processed = estimator.add_event(e);
+            if (processed) {
+                clock_t end_slice = std::clock();
+                std::cout << float(i * 100) / float(ec.size()) << " %\t" << i << "\t"
+                          << (double(end_slice - begin_slice) / CLOCKS_PER_SEC) << " sec\t" << estimator.get_buf_size()
+                          << " events\t" << double(estimator.get_time_diff()) / 1000000000.0 << " slice_td\t"
+                          << double(estimator.get_buf_time_diff()) / 1000000000.0 << " buffer_td\n";
+                begin_slice = std::clock();
+            }
+        }
+        clock_t end = std::clock();
+        std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;
+    } else {
+        std::cout << "Reading from file... (" << file << ")" << std::endl << std::flush;
+        std::ifstream event_file(file, std::ifstream::in);
+        ull i = 0;
+        double t = 0;
+        uint x = 0, y = 0;
+        bool p = false;
+        double t_0 = 0;   // the earliest timestamp in the file
+        if (event_file >> t_0 >> x >> y >> p) {
+            ++i;
+            Event e(y, x, FROM_SEC(0));
+            estimator.add_event(e);
+        }
+        while (event_file >> t >> x >> y >> p) {
+            t -= t_0;
+            ++i;
+            Event e(y, x, FROM_SEC(t));
+            estimator.add_event(e);
+        }
+        event_file.close();
+        std::cout << "Read and processed " << i << " events" << std::endl << std::flush;
+    }
+
+    estimator.recompute();   // ensure that *every* event has been processed
+    estimator.flush();
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    if (!quiet)
+        std::cerr << "slices " << estimator.slices_done() << ", slice-events " << estimator.events_done() << ", GD steps "
+                  << estimator.iterations_done() << ", wall " << wall << " s" << std::endl;
+
+    if (outFileName != NULL) {
+        LinearEventCloudTemplate<Event> accumulated = estimator.get_accumulated();
+        EventFile::to_file_uv(&accumulated, outFileName);
+    }
+    CudaDriver::shutdown();
+    return 0;
+}

@@ -180,6 +180,11 @@ int bf_fast_model(bf_ctx *ctx, int n, const double *pr_x, const double *pr_y, co
                   const uint8_t *noise, int w, int h, int scale, int x_sh, int y_sh,
                   double *out7, float *gx, float *gy);
 
+/* AccelLib::fast_model(ObjectModel&, cv::Mat&) on a caller-supplied mean-timestamp image
+ * (accel_lib.h:337-398 -> object_model.cpp:4-39,103-126) and AccelLib::Sobel (accel_lib.h:400-434):
+ * img is rows x cols f32 row-major.  out7 (nullable) = cx, cy, dx, dy, rot, div, cnt; gx/gy nullable. */
+int bf_model_from_image(bf_ctx *ctx, int rows, int cols, const float *img, double *out7, float *gx, float *gy);
+
 /* AccelLib::project_4param_reinit (accel_lib.h:263-267 -> event.h:99-110,164-168), in place on
  * pr_x/pr_y; nx/ny nullable outputs. */
 int bf_project(bf_ctx *ctx, int n, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,

@@ -179,3 +179,42 @@ def test_large_sensor(oracle_port):
         assert np.all(rel(got["model"][7:9], ref["model"][7:9]) < REL_CONTRACT)
     finally:
         c.close()
+
+
+# ---- against the golden vectors minted from the compiled reference --------------------------------
+from helpers import case_events, golden as _golden, unhex as _unhex  # noqa: E402
+
+_G, _EV = _golden()
+
+
+@pytest.mark.parametrize("case", _G["cases"], ids=[c["name"] for c in _G["cases"]])
+def test_cuda_matches_reference_golden(case):
+    import better_flow_b200 as bf
+    fx, fy, t, noise, init = case_events(case)
+    c = bf.Context(case["rows"], case["cols"], 5, max_events=1 << 18, max_slices=4, device=0)
+    try:
+        got = c.minimize(fx, fy, t, scale=case["scale"], max_iter=case["max_iter"], init=init, noise=noise)
+    finally:
+        c.close()
+    want = _unhex(case["model"])
+    assert got["rc"] == case["rc"]
+    assert got["iters"] == case["iters"]
+    assert [float(v) for v in got["dividers"]] == case["dividers"]
+    for k in ("x_min", "x_max", "y_min", "y_max", "img_rows", "img_cols", "x_shift", "y_shift"):
+        assert got[k] == case["setup"][k], k
+    if case["rc"] == 0:
+        assert got["model"][6] == want[6]
+        assert np.all(rel(got["model"][7:9], want[7:9]) < REL_CONTRACT), rel(got["model"][7:9], want[7:9])
+        assert np.all(rel(got["model"][9:11], want[9:11]) < 1e-3)
+
+
+def test_model_from_image_matches_oracle(ctx240, oracle_port):
+    sl = slices_240(81, 0.01, 1)[0]
+    su = oracle_port.setup_slice(sl.fr_x, sl.fr_y, 180, 240, 3)
+    img = oracle_port.time_img(sl.fr_x.astype(np.float64), sl.fr_y.astype(np.float64), sl.t_ns, su.wsize_x, su.wsize_y, 3,
+                               int(su.x_shift), int(su.y_shift), accum_mode=0)
+    got7, gx, gy = ctx240.model_from_image(img, want_grad=True)
+    w7, wgx, wgy = oracle_port.model(img, want_grad=True)
+    assert np.array_equal(gx, wgx) and np.array_equal(gy, wgy)
+    assert got7[0] == w7[0] and got7[1] == w7[1] and got7[6] == w7[6]
+    assert np.all(rel(got7[2:6], w7[2:6]) < 1e-10)

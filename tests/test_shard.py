@@ -1,0 +1,72 @@
+"""Multi-rank host logic on CPU: 2 processes, gloo backend (SURVEY 8(e) / tier note 5).  The
+partition + single-gather path is exercised with the oracle standing in for the GPU minimiser."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from better_flow_b200 import shard, synth
+
+
+def test_partition_is_a_block_cyclic_cover():
+    for n in (0, 1, 7, 64, 65, 297):
+        for world in (1, 2, 4, 8):
+            parts = [shard.partition(n, world, r) for r in range(world)]
+            flat = sorted(i for p in parts for i in p)
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from oracle import port as oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    st = synth.make_stream(240, 180, 1.5e6, 0.06, seed=13)
+    slices = synth.cut_slices(st, 0.01)
+
+    def minimise(batch):
+        return [dict(oracle.minimize(s.fr_x, s.fr_y, s.t_ns, max_iter=4, accum_mode=1), n_events=len(s.fr_x), flags=0)
+                for s in batch]
+
+    rec = shard.run_sharded(slices, minimise, dist, block=1)
+    q.put((rank, rec))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_shard_and_gather(oracle_port):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=150) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    # single-process answer
+    st = synth.make_stream(240, 180, 1.5e6, 0.06, seed=13)
+    slices = synth.cut_slices(st, 0.01)
+    want = np.stack([oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, max_iter=4, accum_mode=1)["model"] for s in slices])
+    for rank in (0, 1):
+        rec = got[rank]
+        assert rec.shape[0] == len(slices)
+        assert list(rec[:, 0].astype(int)) == list(range(len(slices)))
+        assert np.array_equal(rec[:, 5:16], want)
+        assert np.all(rec[:, 2] == 5)
