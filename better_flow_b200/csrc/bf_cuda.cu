@@ -40,7 +40,8 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
                           int rank) {
     u64 *img0 = P.images + (size_t)group * 2 * P.img_elems;
     u64 *img1 = img0 + P.img_elems;
-    unsigned *flags = P.flags + (size_t)group * P.flag_elems;
+    unsigned *flags0 = P.flags + (size_t)group * 2 * P.flag_elems;
+    unsigned *flags1 = flags0 + P.flag_elems;
     double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
     const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
 
@@ -67,9 +68,11 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     for (int iter = 0;; ++iter) {
         u64 *img_new = buf ? img1 : img0;
         u64 *img_old = buf ? img0 : img1;
+        unsigned *flags_new = buf ? flags1 : flags0;
+        unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
-        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new,
-                       iter > 0 ? img_old : nullptr, nullptr, flags, tag);
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new, nullptr,
+                       flags_new, tag);
         if (pf) __syncthreads();
         PF_MARK(PF_EVENT);
         {
@@ -80,8 +83,8 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
 
         Acc acc;
         acc_zero(acc);
-        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags, tag, rank, P.G, S.list, S.scan, nullptr,
-                              nullptr, nullptr);
+        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags_new, tag, rank, P.G, S.list, S.scan, nullptr,
+                              nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1);
         if (pf) __syncthreads();
         PF_MARK(PF_CELLS);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
@@ -105,9 +108,17 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         if (!S.cont) break;
         buf ^= 1;
     }
-    // Last re-projection of iteration_step (optimizer_rolling.h:340-344) + clearing of the live image.
-    event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, P.want_events != 0, nullptr, buf ? img1 : img0,
-                   P.want_events ? P.nxy : nullptr, flags, tag);
+    // Zero the cells of the image that is still live (its readers all passed barrier B; the next
+    // slice's first splat comes two group barriers later).
+    {
+        Acc none;
+        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, nullptr, 0u, rank, P.G, S.list, S.scan, nullptr, nullptr,
+                              nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag);
+    }
+    // Last re-projection of iteration_step (optimizer_rolling.h:340-344): only needed when the caller
+    // wants the per-event state back (writeout_events).
+    if (P.want_events)
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, true, nullptr, P.nxy, nullptr, 0u);
     if (pf) __syncthreads();
     PF_MARK(PF_FINAL);
     if (prof) pf[PF_SLICES] += 1;
@@ -221,11 +232,11 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
                 bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
             }
             __syncthreads();
-            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, nullptr, P.nxy, nullptr, 0u);
+            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, P.nxy, nullptr, 0u);
         } else if (guard != 0 && P.want_events) {
             BfProj none;
             none.dnx = none.dny = none.cx = none.cy = none.div = none.s = 0; none.c = 1;
-            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, nullptr, P.nxy, nullptr, 0u);
+            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, P.nxy, nullptr, 0u);
         }
         __syncthreads();
 
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StagePar
     Acc acc;
     acc_zero(acc);
     image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, P.flags, P.tag, blockIdx.x, gridDim.x, S.list, S.scan,
-                         P.out_img, P.out_gx, P.out_gy);
+                         P.out_img, P.out_gx, P.out_gy, nullptr, nullptr, 0u);
     acc_block_reduce(acc, S.red, P.partials + blockIdx.x * BF_NSUMS);
 }
 
@@ -507,7 +518,7 @@ static void pick_launch(bf_ctx *c, int n_slices, int *G, int *n_groups) {
 static int next_tag_base(bf_ctx *c, unsigned *tag_base) {
     c->launch_seq += 1;
     if (c->launch_seq >= 4096u) {
-        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)c->n_groups_alloc * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)c->n_groups_alloc * 2 * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
         c->launch_seq = 1;
     }
     *tag_base = c->launch_seq << 20;
@@ -527,8 +538,8 @@ static int configure(bf_ctx *c, int n_slices) {
         c->images_bytes = (size_t)want * 2 * (size_t)c->img_elems * sizeof(u64);
         CU(cudaMalloc(&c->d_images, c->images_bytes));
         CU(cudaMemsetAsync(c->d_images, 0, c->images_bytes, c->stream));
-        CU(cudaMalloc(&c->d_flags, (size_t)want * (size_t)c->flag_elems * sizeof(unsigned)));
-        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)want * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
+        CU(cudaMalloc(&c->d_flags, (size_t)want * 2 * (size_t)c->flag_elems * sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->d_flags, 0, (size_t)want * 2 * (size_t)c->flag_elems * sizeof(unsigned), c->stream));
         c->launch_seq = 0;
         c->ctrl_bytes = 256 + (size_t)want * sizeof(GroupWs);
         CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));

@@ -8,8 +8,10 @@
 //            reference's s x s splat (accel_lib.h:160-165) is recovered exactly in the image pass
 //            as an s x s box sum of the point image (integer sums are associative).  A zero border
 //            of BF_BORDER pixels surrounds the image so patch loads never need bounds checks.
-//   Two such images per CTA group: iteration k splats into image k&1 while the events clear
-//   their iteration k-1 pixels in the other one, so the image pass is read-only.
+//   Two such images (and flag arrays) per CTA group: iteration k splats into image k&1; the image
+//   pass of iteration k reads image k&1 and, in passing, zeroes the cells of image (k-1)&1 that
+//   were live one iteration earlier (coalesced row stores), so every image is all-zero again
+//   before it is splatted into the next time.
 //   flags    u32[cells]         one generation tag per 8 x (32-2H) pixel cell: an event stamps the
 //            current iteration's tag on every cell whose haloed patch contains its pixel; the image
 //            pass visits only cells carrying the current tag (the image is 1-5 % occupied).
@@ -77,7 +79,7 @@ struct KParams {
     u64 *images;             // [n_groups][2][img_elems]
     long long img_elems;
     int pitch;               // elements per stored image row
-    unsigned *flags;         // [n_groups][flag_elems] per-cell generation tags
+    unsigned *flags;         // [n_groups][2][flag_elems] per-cell generation tags, one array per image
     long long flag_elems;
     unsigned tag_base;       // launch sequence number << 20: tags are never reused, so flags need no clearing
     int G;                   // CTAs per group
@@ -217,7 +219,6 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
 //   first     : pr state does not exist yet (pr = fr, Event::reset, event.h:54-59)
 //   project   : apply the warp `q` before splatting
 //   img_new   : image receiving this iteration's splats (may be null: final pass)
-//   img_old   : image holding the previous iteration's splats, cleared here (may be null)
 //   out_nxy   : when non-null, nx/ny are written (final pass for writeout_events)
 // Two events per thread per trip with all loads issued up front: the pass is latency-bound
 // (one L2 round trip per event otherwise), not bandwidth-bound.
@@ -227,7 +228,7 @@ struct EventCtx {
     int cnt_shift, tq, t_min;
     int n_ci, n_cj;
     bool first, project;
-    u64 *img_new, *img_old;
+    u64 *img_new;
     unsigned *flags;
     unsigned tag;
 };
@@ -243,7 +244,6 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, double2 st
     if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }
     else { prx = st.x; pry = st.y; }
     int x, y;
-    if (c.img_old != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) c.img_old[pixel_offset(x, y, c.pm.pitch)] = 0ull;
     double ex = 0.0, ey = 0.0;
     if (c.project) project_event(prx, pry, ex, ey, (float)frx_u, (float)fry_u, (float)t, c.q);
     if (c.project || c.first) *pr_slot = make_double2(prx, pry);
@@ -258,7 +258,7 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, double2 st
 template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, bool first, bool project, u64 *img_new,
-                           u64 *img_old, double2 *out_nxy, unsigned *flags, unsigned tag) {
+                           double2 *out_nxy, unsigned *flags, unsigned tag) {
     typedef CellCfg<SH> C;
     const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
     const int lo = rank * per;
@@ -273,7 +273,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     c.cnt_shift = pk.cnt_shift; c.tq = pk.q; c.t_min = pk.t_min;
     c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
     c.n_cj = (g.cols + C::CW - 1) / C::CW;
-    c.first = first; c.project = project; c.img_new = img_new; c.img_old = img_old; c.flags = flags; c.tag = tag;
+    c.first = first; c.project = project; c.img_new = img_new; c.flags = flags; c.tag = tag;
     for (int i = (int)threadIdx.x; i < cnt; i += 2 * BF_NT) {
         const int k = i + BF_NT;
         const bool two = k < cnt;
@@ -422,51 +422,74 @@ __device__ void acc_block_reduce(const Acc &a, double *sred /* [BF_NW][BF_NSUMS]
     __syncthreads();
 }
 
-// Image pass of one CTA.  The cell flags are scanned in chunks of BF_LIST_CAP; every CTA of the
-// group builds the same compacted list of live cells (index order => deterministic) and its
-// warps take entries  rank*NW + warp, += G*NW.  No CTA barrier inside the cell loop.
+// Compact the cells of [base, base + BF_LIST_CAP) whose flag carries `tag` into `list` (chunk-relative
+// indices, ascending => deterministic).  Every CTA of the group builds the same list.  Returns the count.
+__device__ __forceinline__ int compact_cells(const unsigned *flags, unsigned tag, int base, int n_cells,
+                                             unsigned short *list, int *scan) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PER = BF_LIST_CAP / BF_NT;   // flags per thread per chunk
+    unsigned live = 0;
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = base + (int)threadIdx.x * PER + k;
+        if (c < n_cells && __ldcg(flags + c) == tag) { live |= 1u << k; ++mine; }
+    }
+    int incl = mine;
+    __syncwarp();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    __syncthreads();   // the previous list has been fully consumed
+    if (lane == 31) scan[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int w = 0; w < warp; ++w) off += scan[w];
+    int total = 0;
+    for (int w = 0; w < BF_NW; ++w) total += scan[w];
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+        if (live & (1u << k)) list[off++] = (unsigned short)((int)threadIdx.x * PER + k);
+    __syncthreads();
+    return total;
+}
+
+// Image pass of one CTA: the warps take live cells  rank*NW + warp, += G*NW  of the compacted list
+// (no CTA barrier inside the cell loop).  When img_clear is given, the cells that were live in the
+// OTHER image one iteration ago (flags_clear == tag_clear) get their 8 x CW interior zeroed with
+// coalesced row stores -- every splatted pixel lies in the interior of a cell it stamped.
 template <int SH, bool MATERIALISE>
 __device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
                            const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
-                           int *scan, float *out_img, float *out_gx, float *out_gy) {
+                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
+                           const unsigned *flags_clear, unsigned tag_clear) {
     typedef CellCfg<SH> C;
     const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
     const int n_cells = n_ci * n_cj;
     const int i0 = g.rows / 2, j0 = g.cols / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int PER = BF_LIST_CAP / BF_NT;   // flags per thread per chunk
     for (int base = 0; base < n_cells; base += BF_LIST_CAP) {
-        // ---- compact the live cells of this chunk -----------------------------------------------
-        unsigned live = 0;
-        int mine = 0;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int c = base + (int)threadIdx.x * PER + k;
-            if (c < n_cells && __ldcg(flags + c) == tag) { live |= 1u << k; ++mine; }
+        if (img != nullptr) {
+            const int total = compact_cells(flags, tag, base, n_cells, list, scan);
+            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                const int c = base + (int)list[k];
+                const int ci = c / n_cj, cj = c - ci * n_cj;
+                cell_process<SH, MATERIALISE>(acc, img, pitch, pk, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+            }
         }
-        int incl = mine;
-        __syncwarp();
+        if (img_clear != nullptr) {
+            const int total = compact_cells(flags_clear, tag_clear, base, n_cells, list, scan);
+            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                const int c = base + (int)list[k];
+                const int ci = c / n_cj, cj = c - ci * n_cj;
+                if (lane < C::CW) {
+                    u64 *p = img_clear + (long long)(ci * BF_CELL_ROWS + BF_BORDER) * pitch + (cj * C::CW + BF_BORDER + lane);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        __syncthreads();   // previous chunk's list fully consumed
-        if (lane == 31) scan[warp] = incl;
-        __syncthreads();
-        int off = incl - mine;
-        for (int w = 0; w < warp; ++w) off += scan[w];
-        int total = 0;
-        for (int w = 0; w < BF_NW; ++w) total += scan[w];
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-            if (live & (1u << k)) list[off++] = (unsigned short)((int)threadIdx.x * PER + k);
-        __syncthreads();
-        // ---- process them ---------------------------------------------------------------------------
-        for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
-            const int c = base + (int)list[k];
-            const int ci = c / n_cj, cj = c - ci * n_cj;
-            cell_process<SH, MATERIALISE>(acc, img, pitch, pk, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+                    for (int r = 0; r < BF_CELL_ROWS; ++r) p[(long long)r * pitch] = 0ull;
+                }
+            }
         }
     }
 }
