@@ -447,7 +447,8 @@ struct bf_ctx {
     bf_slice_result *h_results = nullptr;
     // device
     bf_event *d_events = nullptr;
-    double2 *d_pr = nullptr;
+    float2 *d_state = nullptr;
+    double2 *d_pr_out = nullptr;
     double2 *d_nxy = nullptr;
     SliceDesc *d_slices = nullptr;
     bf_slice_result *d_results = nullptr;
@@ -613,7 +614,7 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaMallocHost(&c->h_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMallocHost(slices)", e);
     if ((e = cudaMallocHost(&c->h_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMallocHost(results)", e);
     if ((e = cudaMalloc(&c->d_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMalloc(events)", e);
-    if ((e = cudaMalloc(&c->d_pr, (size_t)max_events * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc(pr)", e);
+    if ((e = cudaMalloc(&c->d_state, (size_t)max_events * sizeof(float2))) != cudaSuccess) return bail("cudaMalloc(state)", e);
     if ((e = cudaMalloc(&c->d_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMalloc(slices)", e);
     if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
 
@@ -630,7 +631,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
-    cudaFree(c->d_events); cudaFree(c->d_pr); cudaFree(c->d_nxy); cudaFree(c->d_slices);
+    cudaFree(c->d_events); cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy); cudaFree(c->d_slices);
     cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
     cudaFree(c->d_stage); cudaFree(c->d_prof);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -778,10 +779,14 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
     if (c->n_slices == 0) { c->ran = true; return BF_OK; }
     int rc = configure(c, c->n_slices);
     if (rc != BF_OK) return rc;
-    if (want_events && !c->d_nxy) CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
+    if (want_events && !c->d_nxy) {
+        CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
+        CU(cudaMalloc(&c->d_pr_out, (size_t)c->max_events * sizeof(double2)));
+    }
     CU(cudaMemsetAsync(c->d_ctrl, 0, c->ctrl_bytes, c->stream));
     KParams P;
-    P.events = c->d_events; P.pr = c->d_pr; P.nxy = want_events ? c->d_nxy : nullptr;
+    P.events = c->d_events; P.state = c->d_state;
+    P.nxy = want_events ? c->d_nxy : nullptr; P.pr_out = want_events ? c->d_pr_out : nullptr;
     P.slices = c->d_slices; P.results = c->d_results; P.n_slices = c->n_slices;
     P.queue = reinterpret_cast<int *>(c->d_ctrl);
     P.ws = reinterpret_cast<GroupWs *>(c->d_ctrl + 256);
@@ -857,7 +862,7 @@ int bf_batch_events(bf_ctx *c, int slot, double *pr_x, double *pr_y, double *nx,
     std::vector<double2> tmp((size_t)d.n);
     CU(cudaStreamSynchronize(c->stream));
     if (pr_x || pr_y) {
-        CU(cudaMemcpy(tmp.data(), c->d_pr + d.ev_off, (size_t)d.n * sizeof(double2), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(tmp.data(), c->d_pr_out + d.ev_off, (size_t)d.n * sizeof(double2), cudaMemcpyDeviceToHost));
         for (int i = 0; i < d.n; ++i) { if (pr_x) pr_x[i] = tmp[i].x; if (pr_y) pr_y[i] = tmp[i].y; }
     }
     if (nx || ny) {

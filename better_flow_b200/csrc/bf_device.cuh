@@ -2,7 +2,10 @@
 //
 // Data layout in HBM / L2:
 //   events   bf_event[n]        8 B/event, read-only, ld.global.nc
-//   pr       double2[n]         warped position state carried between iterations (event.h:100)
+//   state    float2[n]          (float(nx), float(ny)) carried between iterations: the warped position
+//            pr that the next re-projection starts from (event.h:100) depends on the direction
+//            vector only through these two f32 values (event.h:164-168), so pr is recomputed
+//            exactly instead of being stored as two doubles
 //   image    u64[rows_alloc][pitch]  the POINT image: every event adds ONE packed word
 //            (count | sum of t) at its centre pixel with one 64-bit integer atomic.  The
 //            reference's s x s splat (accel_lib.h:160-165) is recovered exactly in the image pass
@@ -68,7 +71,8 @@ struct GroupWs {
 
 struct KParams {
     const bf_event *events;
-    double2 *pr;             // state
+    float2 *state;           // (float(nx), float(ny)) per event
+    double2 *pr_out;         // optional output (pr_x, pr_y), may be null
     double2 *nxy;            // optional output (nx, ny), may be null
     const SliceDesc *slices;
     bf_slice_result *results;
@@ -147,6 +151,13 @@ __device__ __forceinline__ double div_const(double a, double b, double r) {
     return __fma_rn(rem, r, q0);
 }
 
+// Event::apply_project (event.h:164-168) for one coordinate:  k = float(n) / nz  (f64 divide, rounded
+// to f32);  pr = float(fr) - k * float(t) / 10000.0  (f32 multiply, f64 divide, f64 subtract).
+__device__ __forceinline__ double warp_from_n(float fn, float fr, float tf) {
+    const float k = (float)div_const((double)fn, 127.0, 1.0 / 127.0);
+    return __dsub_rn((double)fr, div_const((double)__fmul_rn(k, tf), 10000.0, 1.0 / 10000.0));
+}
+
 // Event::project_4param_reinit + apply_project (event.h:99-110,164-168) for one event.
 // All FP64 operations individually rounded (no contraction), in the reference's order.
 __device__ __forceinline__ void project_event(double &prx, double &pry, double &ex, double &ey,
@@ -158,10 +169,8 @@ __device__ __forceinline__ void project_event(double &prx, double &pry, double &
     const double dy = __dadd_rn(__dmul_rn(-qy, q.div), __dsub_rn(qy, ry));
     ex = __dadd_rn(dx, q.dnx);                                                                  // :107
     ey = __dadd_rn(dy, q.dny);                                                                  // :108
-    const float kx = (float)div_const((double)(float)ex, 127.0, 1.0 / 127.0);                   // :164
-    const float ky = (float)div_const((double)(float)ey, 127.0, 1.0 / 127.0);
-    prx = __dsub_rn((double)frx, div_const((double)__fmul_rn(kx, tf), 10000.0, 1.0 / 10000.0)); // :167
-    pry = __dsub_rn((double)fry, div_const((double)__fmul_rn(ky, tf), 10000.0, 1.0 / 10000.0));
+    prx = warp_from_n((float)ex, frx, tf);
+    pry = warp_from_n((float)ey, fry, tf);
 }
 
 // Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158):
@@ -234,19 +243,22 @@ struct EventCtx {
 };
 
 template <int SH>
-__device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, double2 st, double2 *pr_slot, double2 *nxy_slot) {
+__device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 st, float2 *st_slot, double2 *pr_slot,
+                                          double2 *nxy_slot) {
     const unsigned frx_u = e.x & 0xffffu;
     const unsigned fry_raw = e.x >> 16;
     const bool noise = (fry_raw & BF_EVENT_NOISE) != 0;
     const unsigned fry_u = fry_raw & 0x7fffu;
     const int t = (int)e.y;
+    const float frx = (float)frx_u, fry = (float)fry_u, tf = (float)t;
     double prx, pry;
-    if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }
-    else { prx = st.x; pry = st.y; }
+    if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }                     // Event::reset (event.h:54-59)
+    else { prx = warp_from_n(st.x, frx, tf); pry = warp_from_n(st.y, fry, tf); }   // = the pr computed last time
     int x, y;
     double ex = 0.0, ey = 0.0;
-    if (c.project) project_event(prx, pry, ex, ey, (float)frx_u, (float)fry_u, (float)t, c.q);
-    if (c.project || c.first) *pr_slot = make_double2(prx, pry);
+    if (c.project) project_event(prx, pry, ex, ey, frx, fry, tf, c.q);
+    if (st_slot != nullptr && (c.project || c.first)) *st_slot = make_float2((float)ex, (float)ey);
+    if (pr_slot != nullptr) *pr_slot = make_double2(prx, pry);
     if (nxy_slot != nullptr) *nxy_slot = make_double2(ex, ey);
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
@@ -265,8 +277,9 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     const int cnt = min(sd.n, lo + per) - lo;
     if (cnt <= 0) return;
     const bf_event *ev = P.events + sd.ev_off + lo;
-    double2 *pr = P.pr + sd.ev_off + lo;
+    float2 *state = P.state + sd.ev_off + lo;
     double2 *nxy = out_nxy ? out_nxy + sd.ev_off + lo : nullptr;
+    double2 *pro = out_nxy ? P.pr_out + sd.ev_off + lo : nullptr;   // per-event outputs come as a pair
     EventCtx c;
     make_pixel_map(c.pm, g, P.pitch);
     c.q = q;
@@ -280,13 +293,15 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         const uint2 e0 = ld_nc_u32x2(ev + i);
         uint2 e1 = make_uint2(0u, 0u);
         if (two) e1 = ld_nc_u32x2(ev + k);
-        double2 s0 = make_double2(0.0, 0.0), s1 = s0;
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0;
         if (!first) {
-            s0 = pr[i];
-            if (two) s1 = pr[k];
+            s0 = state[i];
+            if (two) s1 = state[k];
         }
-        event_one<SH>(c, e0, s0, pr + i, nxy ? nxy + i : nullptr);
-        if (two) event_one<SH>(c, e1, s1, pr + k, nxy ? nxy + k : nullptr);
+        // the final pass (no splat) only reads the state; every other pass rewrites it
+        float2 *w0 = img_new ? state + i : nullptr, *w1 = img_new ? state + k : nullptr;
+        event_one<SH>(c, e0, s0, w0, pro ? pro + i : nullptr, nxy ? nxy + i : nullptr);
+        if (two) event_one<SH>(c, e1, s1, w1, pro ? pro + k : nullptr, nxy ? nxy + k : nullptr);
     }
 }
 
