@@ -287,21 +287,37 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
     c.n_cj = (g.cols + C::CW - 1) / C::CW;
     c.first = first; c.project = project; c.img_new = img_new; c.flags = flags; c.tag = tag;
-    for (int i = (int)threadIdx.x; i < cnt; i += 2 * BF_NT) {
+    // software pipeline: the loads of trip n+1 are issued before trip n is processed
+    int i = (int)threadIdx.x;
+    uint2 e0 = make_uint2(0u, 0u), e1 = e0;
+    float2 s0 = make_float2(0.0f, 0.0f), s1 = s0;
+    if (i < cnt) {
+        e0 = ld_nc_u32x2(ev + i);
+        if (!first) s0 = state[i];
+        if (i + BF_NT < cnt) {
+            e1 = ld_nc_u32x2(ev + i + BF_NT);
+            if (!first) s1 = state[i + BF_NT];
+        }
+    }
+    for (; i < cnt; i += 2 * BF_NT) {
         const int k = i + BF_NT;
         const bool two = k < cnt;
-        const uint2 e0 = ld_nc_u32x2(ev + i);
-        uint2 e1 = make_uint2(0u, 0u);
-        if (two) e1 = ld_nc_u32x2(ev + k);
-        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0;
-        if (!first) {
-            s0 = state[i];
-            if (two) s1 = state[k];
+        const int ni = i + 2 * BF_NT, nk = ni + BF_NT;
+        uint2 n0 = make_uint2(0u, 0u), n1 = n0;
+        float2 t0 = make_float2(0.0f, 0.0f), t1 = t0;
+        if (ni < cnt) {
+            n0 = ld_nc_u32x2(ev + ni);
+            if (!first) t0 = state[ni];
+            if (nk < cnt) {
+                n1 = ld_nc_u32x2(ev + nk);
+                if (!first) t1 = state[nk];
+            }
         }
         // the final pass (no splat) only reads the state; every other pass rewrites it
         float2 *w0 = img_new ? state + i : nullptr, *w1 = img_new ? state + k : nullptr;
         event_one<SH>(c, e0, s0, w0, pro ? pro + i : nullptr, nxy ? nxy + i : nullptr);
         if (two) event_one<SH>(c, e1, s1, w1, pro ? pro + k : nullptr, nxy ? nxy + k : nullptr);
+        e0 = n0; e1 = n1; s0 = t0; s1 = t1;
     }
 }
 
