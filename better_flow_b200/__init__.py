@@ -58,6 +58,7 @@ ABI_SYMBOLS = (
     "bf_batch_sync", "bf_batch_run", "bf_batch_time_launches", "bf_ctx_launch_count", "bf_batch_size",
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
     "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile", "bf_model_from_image",
+    "bf_batch_run_streamed",
 )
 
 _lib = None
@@ -95,6 +96,7 @@ def load() -> C.CDLL:
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.bf_batch_launch.argtypes = [C.c_void_p, C.c_int]
         lib.bf_batch_run.argtypes = [C.c_void_p, C.c_int]
+        lib.bf_batch_run_streamed.argtypes = [C.c_void_p, C.c_int]
         lib.bf_batch_time_launches.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         lib.bf_batch_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(SliceResult)]
         lib.bf_batch_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -237,6 +239,10 @@ class Context:
 
     def run(self, want_events=False):
         self._chk(self.lib.bf_batch_run(self.h, 1 if want_events else 0))
+
+    def run_streamed(self, want_events=False):
+        """Asynchronous upload (streamed, overlapped) + launch + download; call sync() afterwards."""
+        self._chk(self.lib.bf_batch_run_streamed(self.h, 1 if want_events else 0))
 
     def time_launches(self, reps, want_events=False) -> float:
         ms = C.c_float(0)

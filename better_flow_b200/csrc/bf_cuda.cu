@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
         // ---- fetch the next slice for this group ------------------------------------------------
         if (rank == 0 && threadIdx.x == 0) {
             const int s = atomicAdd(P.queue, 1);
+            // streamed upload: the copy engine is still filling the event buffer in slice order; wait
+            // until this slice has landed (the counter is written by a copy that follows the data)
+            if (P.ready != nullptr && s < P.n_slices)
+                while (ld_relaxed_u32(P.ready) <= (unsigned)s) __nanosleep(200);
             int *bb = ws->bbox[parity];
             bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; bb[4] = INT_MAX; bb[5] = INT_MIN;
             ws->cur_slice = s;
@@ -423,6 +427,11 @@ struct bf_ctx {
     int max_slices = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of the streamed upload
+    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
+    unsigned *d_ready = nullptr;          // slices uploaded so far (device), fed from h_ready (pinned)
+    unsigned *h_ready = nullptr;
+    int upload_chunks = 8;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // options
@@ -597,6 +606,11 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if (!prop.cooperativeLaunch) { fail(BF_ERR_CUDA, "device lacks cooperative launch"); bf_ctx_destroy(c); return nullptr; }
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     c->stream = c->own_stream;
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&c->d_ready, 256)) != cudaSuccess) return bail("cudaMalloc(ready)", e);
+    if ((e = cudaMallocHost(&c->h_ready, 64 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMallocHost(ready)", e);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
 
@@ -637,6 +651,10 @@ void bf_ctx_destroy(bf_ctx *c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    cudaFree(c->d_ready); cudaFreeHost(c->h_ready);
     delete c;
 }
 
@@ -648,6 +666,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "min_group")) c->min_group = (int)std::max(1LL, value);
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
+    else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
     else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = value >= 2 ? 2 : 1;
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
     return BF_OK;
@@ -772,9 +791,50 @@ int bf_batch_upload(bf_ctx *c) {
     return BF_OK;
 }
 
+static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready);
+
 int bf_batch_launch(bf_ctx *c, int want_events) {
     if (!c) return fail(BF_ERR_ARG, "null context");
     if (!c->uploaded) return fail(BF_ERR_STATE, "bf_batch_launch before bf_batch_upload");
+    return launch_impl(c, want_events, nullptr);
+}
+
+// upload -> launch -> download with the event upload STREAMED: the slice table goes first, the kernel
+// is launched at once, and the events follow in slice-ordered chunks on a second stream while the
+// first slices are already being minimised (each chunk is followed by a 4-byte copy that bumps the
+// device-side "slices uploaded" counter the kernel polls).  Asynchronous; pair with bf_batch_sync.
+int bf_batch_run_streamed(bf_ctx *c, int want_events) {
+    if (!c) return fail(BF_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (c->n_slices == 0) { c->uploaded = c->ran = true; return BF_OK; }
+    // the copy stream must not overtake work still queued on the compute stream (previous batch)
+    CU(cudaEventRecord(c->ev_done, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
+    CU(cudaMemsetAsync(c->d_ready, 0, sizeof(unsigned), c->copy_stream));
+    CU(cudaMemcpyAsync(c->d_slices, c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    // chunk boundaries on slice boundaries (slices are laid out back to back in add order)
+    const int chunks = std::min(c->upload_chunks, c->n_slices);
+    int s0 = 0;
+    for (int k = 0; k < chunks; ++k) {
+        const int s1 = (int)((long long)c->n_slices * (k + 1) / chunks);
+        if (s1 <= s0) continue;
+        const long long lo = c->h_slices[s0].ev_off;
+        const long long hi = c->h_slices[s1 - 1].ev_off + c->h_slices[s1 - 1].n;
+        if (hi > lo)
+            CU(cudaMemcpyAsync(c->d_events + lo, c->h_events + lo, (size_t)(hi - lo) * sizeof(bf_event), cudaMemcpyHostToDevice, c->copy_stream));
+        c->h_ready[k] = (unsigned)s1;
+        CU(cudaMemcpyAsync(c->d_ready, c->h_ready + k, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
+        s0 = s1;
+    }
+    c->uploaded = true;
+    int rc = launch_impl(c, want_events, c->d_ready);
+    if (rc != BF_OK) return rc;
+    return bf_batch_download(c);
+}
+
+static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     CU(cudaSetDevice(c->device));
     if (c->n_slices == 0) { c->ran = true; return BF_OK; }
     int rc = configure(c, c->n_slices);
@@ -795,6 +855,7 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
     if ((rc = next_tag_base(c, &P.tag_base)) != BF_OK) return rc;
     P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
+    P.ready = ready;
     P.prof = nullptr;
     if (c->profile) {
         if (!c->d_prof) CU(cudaMalloc(&c->d_prof, (size_t)1024 * BF_NPROF * sizeof(long long)));

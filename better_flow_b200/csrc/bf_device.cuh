@@ -91,6 +91,7 @@ struct KParams {
     int min_events;          // 1000 (optimizer_rolling.h:57)
     int iter_cap;
     int want_events;
+    const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)
     long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
 };
 #define BF_NPROF 16

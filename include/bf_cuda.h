@@ -139,6 +139,12 @@ int bf_batch_sync(bf_ctx *ctx);
 /* ... and the synchronous composition upload -> launch -> download -> sync. */
 int bf_batch_run(bf_ctx *ctx, int want_events);
 
+/* upload -> launch -> download with the event upload streamed in slice-ordered chunks on a second
+ * stream and overlapped with the minimisation of the slices that have already landed (one
+ * persistent launch).  Requires slices added back to back in order (bf_batch_add / _packed /
+ * _staged with increasing offsets).  Asynchronous: follow with bf_batch_sync. */
+int bf_batch_run_streamed(bf_ctx *ctx, int want_events);
+
 /* Times `reps` back-to-back launches on the resident batch with CUDA events on the context's
  * stream (inputs already in HBM).  Returns total milliseconds in *ms. */
 int bf_batch_time_launches(bf_ctx *ctx, int reps, int want_events, float *ms);

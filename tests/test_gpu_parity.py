@@ -218,3 +218,35 @@ def test_model_from_image_matches_oracle(ctx240, oracle_port):
     assert np.array_equal(gx, wgx) and np.array_equal(gy, wgy)
     assert got7[0] == w7[0] and got7[1] == w7[1] and got7[6] == w7[6]
     assert np.all(rel(got7[2:6], w7[2:6]) < 1e-10)
+
+
+def test_streamed_upload_equals_plain_run():
+    """bf_batch_run_streamed (chunked H2D overlapped with compute inside one launch) gives the very
+    same records as upload -> launch -> download."""
+    import better_flow_b200 as bf
+    st = synth.make_stream(240, 180, 3e6, 0.4, seed=91)
+    sls = synth.cut_slices(st, 0.01)
+    n_ev = sum(len(s.fr_x) for s in sls)
+    c = bf.Context(180, 240, 3, max_events=n_ev + 16, max_slices=len(sls) + 1, device=0)
+    try:
+        for s in sls:
+            c.add(s.fr_x, s.fr_y, s.t_ns, 3, 6)
+        c.run()
+        plain = [r["model"].copy() for r in c.results()]
+        for chunks in (1, 3, 8):
+            c.set_option("upload_chunks", chunks)
+            c.run_streamed()
+            c.sync()
+            for a, r in zip(plain, c.results()):
+                assert np.array_equal(a, r["model"])
+    finally:
+        c.close()
+
+
+def test_permutation_invariance_bit_exact(ctx240):
+    """Integer accumulation makes the result independent of the order of the events -- to the last bit."""
+    sl = slices_240(95, 0.03, 1)[0]
+    a = ctx240.minimize(sl.fr_x, sl.fr_y, sl.t_ns, max_iter=8)
+    perm = np.random.default_rng(2).permutation(len(sl.fr_x))
+    b = ctx240.minimize(sl.fr_x[perm], sl.fr_y[perm], sl.t_ns[perm], max_iter=8)
+    assert a["iters"] == b["iters"] and np.array_equal(a["model"], b["model"])
