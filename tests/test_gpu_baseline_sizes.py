@@ -1,0 +1,108 @@
+"""GPU tests at the sizes BASELINE.json names (configs[2..4]): oracle comparison where the oracle
+finishes in seconds, size-independent properties otherwise (bit-exact invariance under event
+permutation and under batching, integer checksums of the image pass recomputed with numpy)."""
+import numpy as np
+import pytest
+
+import better_flow_b200 as bf
+from better_flow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(b), 1e-300)
+
+
+
+
+def test_config2_davis346_batch_of_64(oracle_port):
+    """configs[2]: DAVIS-346 346x260, 50 ms slices, 64 slices batched per launch."""
+    st = synth.make_stream(346, 260, 2e6, 0.05 * 64, seed=33)
+    sls = synth.cut_slices(st, 0.05)[:64]
+    n_ev = sum(len(s.fr_x) for s in sls)
+    c = bf.Context(260, 346, 3, max_events=n_ev + 16, max_slices=65, device=0)
+    try:
+        for s in sls:
+            c.add(s.fr_x, s.fr_y, s.t_ns, 3, 10)
+        c.run()
+        res = c.results()
+        assert all(r["rc"] == 0 and 1 <= r["iters"] <= 11 for r in res)   # max_iter=10 -> at most 11 steps
+        # oracle on a sample of the batch
+        for k in (0, 31, 63):
+            s = sls[k]
+            exact = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=10, rows=260, cols=346, accum_mode=1)
+            ref = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=10, rows=260, cols=346, accum_mode=0)
+            assert res[k]["iters"] == exact["iters"] == ref["iters"]
+            assert res[k]["model"][6] == exact["model"][6]
+            assert np.all(rel(res[k]["model"][7:11], exact["model"][7:11]) < 1e-9)
+            assert np.all(rel(res[k]["model"][7:9], ref["model"][7:9]) < 1e-4)
+        # every slice: identical to running it alone, and invariant under a permutation of its events
+        rng = np.random.default_rng(0)
+        for k in (5, 40):
+            s = sls[k]
+            alone = c.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=10)
+            p = rng.permutation(len(s.fr_x))
+            shuf = c.minimize(s.fr_x[p], s.fr_y[p], s.t_ns[p], scale=3, max_iter=10)
+            assert np.array_equal(alone["model"], res[k]["model"])
+            assert np.array_equal(shuf["model"], res[k]["model"])
+    finally:
+        c.close()
+
+
+def test_config4_hd_sensor_one_million_events(oracle_port):
+    """configs[4] shape: 1280x720, 10 ms at 100 Mev/s = 1 M events, 2160x3840 image (8.3 Mpx)."""
+    st = synth.make_stream(1280, 720, 100e6, 0.01, seed=44)
+    s = synth.cut_slices(st, 0.01)[0]
+    assert len(s.fr_x) == 1_000_000
+    c = bf.Context(720, 1280, 3, max_events=len(s.fr_x) + 16, max_slices=2, device=0)
+    try:
+        got = c.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=2)
+        exact = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=2, rows=720, cols=1280, accum_mode=1)
+        assert got["rc"] == 0 and got["iters"] == exact["iters"] == 3
+        assert (got["img_rows"], got["img_cols"]) == (2160, 3840)
+        assert got["model"][6] == exact["model"][6]
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < 1e-9)
+        assert not (got["flags"] & bf.FLAG_T_QUANTISED)          # exact packed sums even at 1 M events
+        # integer checksums of the image pass from first principles (numpy), iteration-0 geometry
+        pr_x, pr_y = s.fr_x.astype(np.float64), s.fr_y.astype(np.float64)
+        su = oracle_port.setup_slice(s.fr_x, s.fr_y, 720, 1280, 3)
+        m7 = c.fast_model(pr_x, pr_y, s.t_ns, su.wsize_x, su.wsize_y, 3, int(su.x_shift), int(su.y_shift))
+        x = (pr_x * 3 + int(su.x_shift)).astype(np.int64)
+        y = (pr_y * 3 + int(su.y_shift)).astype(np.int64)
+        # the reference rejects x >= w + scale/2 (accel_lib.h:157): the last sensor row/column never splats
+        keep = (x >= 1) & (x < su.wsize_x + 1) & (y >= 1) & (y < su.wsize_y + 1)
+        x, y = x[keep], y[keep]
+        occ = np.zeros((su.img_rows, su.img_cols), dtype=bool)
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                occ[x + dx, y + dy] = True
+        # mean time > 1 us everywhere here (t >= 0, events per box >= 1, first event at ~0 excluded by tolerance)
+        ii, jj = np.nonzero(occ)
+        assert abs(m7[6] - occ.sum()) <= 2
+        assert abs(m7[0] - ii.mean()) < 1e-3 and abs(m7[1] - jj.mean()) < 1e-3
+    finally:
+        c.close()
+
+
+def test_config3_vga_sharded_batch_is_order_and_grouping_independent():
+    """configs[3] shape: 640x480, 20 ms at 10 Mev/s = 200 k events per slice; a batch of 8 slices gives the
+    same records whatever the CTA grouping (what a different GPU count / batch size would change)."""
+    st = synth.make_stream(640, 480, 10e6, 0.02 * 8, seed=55)
+    sls = synth.cut_slices(st, 0.02)[:8]
+    n_ev = sum(len(s.fr_x) for s in sls)
+    outs = []
+    for group in (0, 16, 74):
+        c = bf.Context(480, 640, 3, max_events=n_ev + 16, max_slices=9, device=0)
+        try:
+            c.set_option("group_size", group)
+            for s in sls:
+                c.add(s.fr_x, s.fr_y, s.t_ns, 3, 10)
+            c.run()
+            outs.append([(r["iters"], r["model"][6]) + tuple(r["model"][7:11]) for r in c.results()])
+        finally:
+            c.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert a[0] == b[0] and a[1] == b[1]
+            assert np.all(rel(a[2:], b[2:]) < 1e-10)      # only the fp64 reduction tree differs with G
