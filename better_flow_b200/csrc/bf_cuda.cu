@@ -388,7 +388,8 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
                                         const BfProj q) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double px = pr_x[i], py = pr_y[i], ex, ey;
-        project_event(px, py, ex, ey, (float)fr_x[i], (float)fr_y[i], (float)t[i], q);
+        float mx, my;
+        project_event(px, py, ex, ey, mx, my, (float)fr_x[i], (float)fr_y[i], (float)t[i], q);
         pr_x[i] = px; pr_y[i] = py;
         if (nx) nx[i] = ex;
         if (ny) ny[i] = ey;

@@ -2,10 +2,10 @@
 //
 // Data layout in HBM / L2:
 //   events   bf_event[n]        8 B/event, read-only, ld.global.nc
-//   state    float2[n]          (float(nx), float(ny)) carried between iterations: the warped position
-//            pr that the next re-projection starts from (event.h:100) depends on the direction
-//            vector only through these two f32 values (event.h:164-168), so pr is recomputed
-//            exactly instead of being stored as two doubles
+//   state    float2[n]          carried between iterations.  The warped position pr that the next
+//            re-projection starts from (event.h:100) is  float(fr) - m / 10000.0  with the f32
+//            product m = k * float(t), k = float(float(n) / nz)  (event.h:164-168), so storing the
+//            two f32 values (m_x, m_y) reproduces pr exactly at half the bytes of two doubles
 //   image    u64[rows_alloc][pitch]  the POINT image: every event adds ONE packed word
 //            (count | sum of t) at its centre pixel with one 64-bit integer atomic.  The
 //            reference's s x s splat (accel_lib.h:160-165) is recovered exactly in the image pass
@@ -71,7 +71,7 @@ struct GroupWs {
 
 struct KParams {
     const bf_event *events;
-    float2 *state;           // (float(nx), float(ny)) per event
+    float2 *state;           // (m_x, m_y) per event, see above
     double2 *pr_out;         // optional output (pr_x, pr_y), may be null
     double2 *nxy;            // optional output (nx, ny), may be null
     const SliceDesc *slices;
@@ -152,16 +152,20 @@ __device__ __forceinline__ double div_const(double a, double b, double r) {
     return __fma_rn(rem, r, q0);
 }
 
-// Event::apply_project (event.h:164-168) for one coordinate:  k = float(n) / nz  (f64 divide, rounded
-// to f32);  pr = float(fr) - k * float(t) / 10000.0  (f32 multiply, f64 divide, f64 subtract).
-__device__ __forceinline__ double warp_from_n(float fn, float fr, float tf) {
-    const float k = (float)div_const((double)fn, 127.0, 1.0 / 127.0);
-    return __dsub_rn((double)fr, div_const((double)__fmul_rn(k, tf), 10000.0, 1.0 / 10000.0));
+// Event::apply_project (event.h:164-168) for one coordinate, in two halves:
+//   m  = k * float(t),  k = float(n) / nz   (f64 divide rounded to f32, then an f32 multiply)
+//   pr = float(fr) - m / 10000.0            (f64 divide, f64 subtract)
+__device__ __forceinline__ float slope_time(double n, float tf) {
+    const float k = (float)div_const((double)(float)n, 127.0, 1.0 / 127.0);
+    return __fmul_rn(k, tf);
+}
+__device__ __forceinline__ double warp_from_m(float m, float fr) {
+    return __dsub_rn((double)fr, div_const((double)m, 10000.0, 1.0 / 10000.0));
 }
 
 // Event::project_4param_reinit + apply_project (event.h:99-110,164-168) for one event.
 // All FP64 operations individually rounded (no contraction), in the reference's order.
-__device__ __forceinline__ void project_event(double &prx, double &pry, double &ex, double &ey,
+__device__ __forceinline__ void project_event(double &prx, double &pry, double &ex, double &ey, float &mx, float &my,
                                               float frx, float fry, float tf, const BfProj &q) {
     const double rx = __dsub_rn(prx, q.cx), ry = __dsub_rn(pry, q.cy);                           // :100
     const double qx = __dsub_rn(__dmul_rn(q.c, rx), __dmul_rn(q.s, ry));                        // :102
@@ -170,8 +174,10 @@ __device__ __forceinline__ void project_event(double &prx, double &pry, double &
     const double dy = __dadd_rn(__dmul_rn(-qy, q.div), __dsub_rn(qy, ry));
     ex = __dadd_rn(dx, q.dnx);                                                                  // :107
     ey = __dadd_rn(dy, q.dny);                                                                  // :108
-    prx = warp_from_n((float)ex, frx, tf);
-    pry = warp_from_n((float)ey, fry, tf);
+    mx = slope_time(ex, tf);
+    my = slope_time(ey, tf);
+    prx = warp_from_m(mx, frx);
+    pry = warp_from_m(my, fry);
 }
 
 // Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158):
@@ -235,7 +241,8 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
 struct EventCtx {
     PixelMap pm;
     BfProj q;
-    int cnt_shift, tq, t_min;
+    u64 one;                 // 1 << cnt_shift: the count field of a packed word
+    int tq, t_min;
     int n_ci, n_cj;
     bool first, project;
     u64 *img_new;
@@ -254,16 +261,17 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 st,
     const float frx = (float)frx_u, fry = (float)fry_u, tf = (float)t;
     double prx, pry;
     if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }                     // Event::reset (event.h:54-59)
-    else { prx = warp_from_n(st.x, frx, tf); pry = warp_from_n(st.y, fry, tf); }   // = the pr computed last time
+    else { prx = warp_from_m(st.x, frx); pry = warp_from_m(st.y, fry); }           // = the pr computed last time
     int x, y;
     double ex = 0.0, ey = 0.0;
-    if (c.project) project_event(prx, pry, ex, ey, frx, fry, tf, c.q);
-    if (st_slot != nullptr && (c.project || c.first)) *st_slot = make_float2((float)ex, (float)ey);
+    float mx = 0.0f, my = 0.0f;
+    if (c.project) project_event(prx, pry, ex, ey, mx, my, frx, fry, tf, c.q);
+    if (st_slot != nullptr && (c.project || c.first)) *st_slot = make_float2(mx, my);
     if (pr_slot != nullptr) *pr_slot = make_double2(prx, pry);
     if (nxy_slot != nullptr) *nxy_slot = make_double2(ex, ey);
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
-        atomicAdd(c.img_new + pixel_offset(x, y, c.pm.pitch), (1ull << c.cnt_shift) + (dt >> c.tq));
+        atomicAdd(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
         mark_cells<SH>(c.flags, c.tag, x, y, c.n_ci, c.n_cj);
     }
 }
@@ -284,7 +292,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     EventCtx c;
     make_pixel_map(c.pm, g, P.pitch);
     c.q = q;
-    c.cnt_shift = pk.cnt_shift; c.tq = pk.q; c.t_min = pk.t_min;
+    c.one = 1ull << pk.cnt_shift; c.tq = pk.q; c.t_min = pk.t_min;
     c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
     c.n_cj = (g.cols + C::CW - 1) / C::CW;
     c.first = first; c.project = project; c.img_new = img_new; c.flags = flags; c.tag = tag;
