@@ -23,7 +23,7 @@
 
 struct __align__(16) Smem {
     double red[BF_NW * BF_NSUMS];
-    unsigned short list[BF_LIST_CAP];
+    unsigned short list[2][BF_LIST_CAP];   // live cells of this iteration / of the previous one
     int scan[BF_NW];
     SliceDesc sd;
     BfGeom g;
@@ -65,6 +65,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         tc = now_;                            \
     }
     int buf = 0;
+    int n_prev = -1;    // live cells of the previous iteration when they are still listed in S.list[buf ^ 1]
     for (int iter = 0;; ++iter) {
         u64 *img_new = buf ? img1 : img0;
         u64 *img_old = buf ? img0 : img1;
@@ -83,8 +84,9 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
 
         Acc acc;
         acc_zero(acc);
-        image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags_new, tag, rank, P.G, S.list, S.scan, nullptr,
-                              nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1);
+        n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags_new, tag, rank, P.G, S.list[buf], S.scan,
+                                       nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
+                                       n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
         if (pf) __syncthreads();
         PF_MARK(PF_CELLS);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
@@ -112,8 +114,9 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     // slice's first splat comes two group barriers later).
     {
         Acc none;
-        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, nullptr, 0u, rank, P.G, S.list, S.scan, nullptr, nullptr,
-                              nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag);
+        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, nullptr, 0u, rank, P.G, S.list[buf ^ 1], S.scan, nullptr,
+                              nullptr, nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag,
+                              n_prev >= 0 ? S.list[buf] : nullptr, n_prev);
     }
     // Last re-projection of iteration_step (optimizer_rolling.h:340-344): only needed when the caller
     // wants the per-event state back (writeout_events).
@@ -306,8 +309,8 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StagePar
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     Acc acc;
     acc_zero(acc);
-    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, P.flags, P.tag, blockIdx.x, gridDim.x, S.list, S.scan,
-                         P.out_img, P.out_gx, P.out_gy, nullptr, nullptr, 0u);
+    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, P.flags, P.tag, blockIdx.x, gridDim.x, S.list[0], S.scan,
+                         P.out_img, P.out_gx, P.out_gy, nullptr, nullptr, 0u, nullptr, -1);
     acc_block_reduce(acc, S.red, P.partials + blockIdx.x * BF_NSUMS);
 }
 

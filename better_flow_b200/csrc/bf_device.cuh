@@ -384,6 +384,10 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
     const bool out_lane = (lane >= C::H) && (lane < 32 - C::H);
     const int j = cj * C::CW + lane - C::H;
     __syncwarp();
+    // per-cell partial sums: the column index j is fixed per lane, so its moments are folded in once
+    // per cell instead of once per pixel
+    int c_cnt = 0, c_si = 0;
+    double c_gx = 0.0, c_gy = 0.0;
     float L0 = __shfl_up_sync(0xffffffffu, A[0], 1), R0 = __shfl_down_sync(0xffffffffu, A[0], 1);
     float L1 = __shfl_up_sync(0xffffffffu, A[1], 1), R1 = __shfl_down_sync(0xffffffffu, A[1], 1);
 #pragma unroll
@@ -394,9 +398,8 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
         const float v = A[r];
         float gx = 0.0f, gy = 0.0f;
         if (out_lane && BF_OCC(v)) {
-            acc.cnt += 1;
-            acc.si += i;
-            acc.sj += j;
+            c_cnt += 1;
+            c_si += i;
             // taps: v(k,l) = T[row-1+l][col-1+k]; column j-1 = (L0,L1,L2), j = (A[r-1],.,A[r+1]), j+1 = (R0,R1,R2)
             if (BF_OCC(L0) && BF_OCC(L1) && BF_OCC(L2) && BF_OCC(A[r - 1]) && BF_OCC(A[r + 1]) && BF_OCC(R0) &&
                 BF_OCC(R1) && BF_OCC(R2)) {
@@ -414,14 +417,12 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
                 b = __fadd_rn(b, __fmul_rn(R2, -3.0f));
                 gx = a;
                 gy = b;
-                const double di = (double)(i - i0), dj = (double)(j - j0);
+                const double di = (double)(i - i0);
                 const double dgx = (double)gx, dgy = (double)gy;
-                acc.sgx += dgx;
-                acc.sgy += dgy;
+                c_gx += dgx;
+                c_gy += dgy;
                 acc.sigx += di * dgx;
-                acc.sjgx += dj * dgx;
                 acc.sigy += di * dgy;
-                acc.sjgy += dj * dgy;
             }
         }
         if (MATERIALISE) {
@@ -433,6 +434,16 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
             }
         }
         L0 = L1; L1 = L2; R0 = R1; R1 = R2;
+    }
+    if (c_cnt != 0) {
+        const double dj = (double)(j - j0);
+        acc.cnt += c_cnt;
+        acc.si += c_si;
+        acc.sj += (long long)j * c_cnt;
+        acc.sgx += c_gx;
+        acc.sgy += c_gy;
+        acc.sjgx += dj * c_gx;
+        acc.sjgy += dj * c_gy;
     }
 }
 
@@ -496,42 +507,65 @@ __device__ __forceinline__ int compact_cells(const unsigned *flags, unsigned tag
     return total;
 }
 
+// Zero the 8 x CW interior of one cell with coalesced row stores (one warp).
+template <int SH>
+__device__ __forceinline__ void cell_clear(u64 *img, int pitch, int ci, int cj) {
+    typedef CellCfg<SH> C;
+    const int lane = threadIdx.x & 31;
+    if (lane < C::CW) {
+        u64 *p = img + (long long)(ci * BF_CELL_ROWS + BF_BORDER) * pitch + (cj * C::CW + BF_BORDER + lane);
+#pragma unroll
+        for (int r = 0; r < BF_CELL_ROWS; ++r) p[(long long)r * pitch] = 0ull;
+    }
+}
+
 // Image pass of one CTA: the warps take live cells  rank*NW + warp, += G*NW  of the compacted list
-// (no CTA barrier inside the cell loop).  When img_clear is given, the cells that were live in the
-// OTHER image one iteration ago (flags_clear == tag_clear) get their 8 x CW interior zeroed with
-// coalesced row stores -- every splatted pixel lies in the interior of a cell it stamped.
+// (no CTA barrier inside the cell loop).
+//
+// Clearing: the cells that were live in the OTHER image one iteration ago get their interior zeroed
+// here (every splatted pixel lies in the interior of a cell it stamped), so that image is all-zero
+// again before it is splatted into.  When the whole cell grid fits one list (n_cells <= BF_LIST_CAP,
+// every sensor up to ~VGA) the previous iteration's compacted list is simply kept in shared memory
+// (`list_prev`, `n_prev`) and no second scan is needed; larger grids re-scan the other flag array.
+// Returns the number of live cells when the grid fits one list (else -1).
 template <int SH, bool MATERIALISE>
-__device__ void image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
-                           const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
-                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
-                           const unsigned *flags_clear, unsigned tag_clear) {
+__device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
+                          const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
+                          int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
+                          const unsigned *flags_clear, unsigned tag_clear, const unsigned short *list_prev,
+                          int n_prev) {
     typedef CellCfg<SH> C;
     const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
     const int n_cells = n_ci * n_cj;
     const int i0 = g.rows / 2, j0 = g.cols / 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool one_chunk = n_cells <= BF_LIST_CAP;
+    int n_live = -1;
     for (int base = 0; base < n_cells; base += BF_LIST_CAP) {
         if (img != nullptr) {
             const int total = compact_cells(flags, tag, base, n_cells, list, scan);
+            if (one_chunk) n_live = total;
             for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
                 const int c = base + (int)list[k];
                 const int ci = c / n_cj, cj = c - ci * n_cj;
                 cell_process<SH, MATERIALISE>(acc, img, pitch, pk, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
             }
         }
-        if (img_clear != nullptr) {
+        if (img_clear != nullptr && !(one_chunk && list_prev != nullptr)) {
             const int total = compact_cells(flags_clear, tag_clear, base, n_cells, list, scan);
             for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
                 const int c = base + (int)list[k];
-                const int ci = c / n_cj, cj = c - ci * n_cj;
-                if (lane < C::CW) {
-                    u64 *p = img_clear + (long long)(ci * BF_CELL_ROWS + BF_BORDER) * pitch + (cj * C::CW + BF_BORDER + lane);
-#pragma unroll
-                    for (int r = 0; r < BF_CELL_ROWS; ++r) p[(long long)r * pitch] = 0ull;
-                }
+                cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
             }
         }
     }
+    if (img_clear != nullptr && one_chunk && list_prev != nullptr) {
+        for (int k = rank * BF_NW + warp; k < n_prev; k += G * BF_NW) {
+            const int c = (int)list_prev[k];
+            cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
+        }
+    }
+    return n_live;
 }
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):

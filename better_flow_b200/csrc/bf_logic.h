@@ -88,7 +88,8 @@ BF_HD unsigned long long bf_pack_value(const BfPack &p, int32_t t) {
 BF_HD float bf_unpack_avg(const BfPack &p, unsigned long long v) {
     const unsigned long long cnt = v >> p.cnt_shift;
     if (cnt == 0) return 0.0f;
-    const long long sum = (long long)((v & p.sum_mask) << p.q) + (long long)cnt * (long long)p.t_min;
+    long long sum = (long long)((v & p.sum_mask) << p.q);
+    if (p.t_min != 0) sum += (long long)cnt * (long long)p.t_min;
     // sum / 1e9 as multiply-by-reciprocal + one fma correction step: equal to the correctly rounded
     // quotient for every integer dividend tried (2e9 random |a| < 2^53, tools/ in DESIGN.md) and
     // ~10x cheaper than an IEEE fp64 divide on the GPU.
