@@ -42,7 +42,7 @@ RATE_EPS = 3e6
 SLICE_S = 0.030
 SCALE = 3
 MAX_ITER = -1
-SLICES_PER_STEP = 296          # 4 slices per CTA group (74 groups); 296 x ~90 k events x 8 B = 213 MB of events > 126 MB L2
+SLICES_PER_STEP = 592          # 4 slices per CTA group (148 groups of 2); 592 x ~90 k events x 8 B = 426 MB of events > 126 MB L2
 METRIC = "Mevents/sec motion-compensated"
 UNIT = "Mevents/s"
 WORKLOAD = ("DAVIS-240C 240x180 synthetic 3 Mev/s contour stream, 30 ms slices (~90k events), "

@@ -440,7 +440,7 @@ struct bf_ctx {
 
     // options
     int opt_group = 0;          // CTAs per slice; 0 = auto (from the batch size)
-    int min_group = 4;          // smallest automatic group
+    int min_group = 2;          // smallest automatic group (measured: 2 >= 3 > 4 > 6 > 1 on DAVIS-240C)
     int ctas_per_sm = 2;        // 1 or 2 resident CTAs per SM
     long long image_budget_mb = 24576;   // cap on the point-image allocation
     int n_groups_alloc = 0;
