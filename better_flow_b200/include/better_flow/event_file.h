@@ -4,8 +4,110 @@
 #ifndef BF_EVENT_FILE_H
 #define BF_EVENT_FILE_H
 
+#include <charconv>
+#include <system_error>
+
 #include <better_flow/common.h>
 #include <better_flow/event.h>
+
+// Block reader for the "t x y p" text format (addition).  The reference parses with
+// `ifstream >> double >> uint >> uint >> bool` (bf_motion_compensator.cpp:190-202, event_file.h:141-176),
+// which costs ~1 us per event -- two orders of magnitude more than the minimisation itself on the GPU.
+// This reader pulls the file in 4 MiB blocks and converts with std::from_chars, which like the
+// strtod behind operator>> is correctly rounded, so every timestamp is the same double.  Same
+// termination rule as the reference loop: reading stops at the first record that does not parse
+// (p must be 0 or 1, as for operator>>(bool)).
+class TextEventReader {
+    FILE *fp_;
+    bool own_;
+    std::vector<char> buf_;
+    size_t pos_, end_;
+    bool eof_, failed_;
+
+    // make sure a whole line (or the rest of the file) is buffered starting at pos_
+    bool fill_line() {
+        for (;;) {
+            const void *nl = pos_ < end_ ? memchr(buf_.data() + pos_, '\n', end_ - pos_) : nullptr;
+            if (nl || eof_) return pos_ < end_;
+            if (pos_ > 0) {
+                memmove(buf_.data(), buf_.data() + pos_, end_ - pos_);
+                end_ -= pos_;
+                pos_ = 0;
+            }
+            if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);   // a line longer than the block
+            const size_t got = fread(buf_.data() + end_, 1, buf_.size() - end_, fp_);
+            end_ += got;
+            if (got == 0) eof_ = true;
+        }
+    }
+    static bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+    void skip_space() {
+        // operator>> skips any whitespace including newlines, so records may span lines
+        for (;;) {
+            while (pos_ < end_ && is_space(buf_[pos_])) ++pos_;
+            if (pos_ < end_ || eof_) return;
+            fill_line();
+            if (pos_ >= end_) return;
+        }
+    }
+    // token = [pos_, first whitespace); guaranteed fully buffered
+    bool token(const char *&b, const char *&e) {
+        skip_space();
+        if (pos_ >= end_) return false;
+        fill_line();
+        size_t q = pos_;
+        while (q < end_ && !is_space(buf_[q])) ++q;
+        b = buf_.data() + pos_;
+        e = buf_.data() + q;
+        pos_ = q;
+        return e > b;
+    }
+    bool get_double(double &v) {
+        const char *b, *e;
+        if (!token(b, e)) return false;
+        if (*b == '+') ++b;
+        const auto r = std::from_chars(b, e, v);
+        return r.ec == std::errc() && r.ptr == e;
+    }
+    bool get_uint(uint &v) {
+        const char *b, *e;
+        if (!token(b, e)) return false;
+        // operator>>(unsigned) follows strtoul: a leading '-' negates the magnitude modulo 2^32
+        const bool neg = *b == '-';
+        if (*b == '+' || neg) ++b;
+        const auto r = std::from_chars(b, e, v);
+        if (r.ec != std::errc() || r.ptr != e) return false;
+        if (neg) v = 0u - v;
+        return true;
+    }
+
+public:
+    explicit TextEventReader(const std::string &fname) : pos_(0), end_(0), eof_(false), failed_(false) {
+        own_ = fname != "-";
+        fp_ = own_ ? fopen(fname.c_str(), "rb") : stdin;
+        buf_.resize(4u << 20);
+        if (!fp_) { eof_ = true; failed_ = true; }
+    }
+    ~TextEventReader() {
+        if (fp_ && own_) fclose(fp_);
+    }
+    TextEventReader(const TextEventReader &) = delete;
+    TextEventReader &operator=(const TextEventReader &) = delete;
+
+    bool opened() const { return fp_ != nullptr; }
+
+    // next "t x y p" record; false at end of input or at the first malformed record
+    bool next(double &t, uint &x, uint &y, bool &p) {
+        if (failed_) return false;
+        uint pv = 0;
+        if (!get_double(t) || !get_uint(x) || !get_uint(y) || !get_uint(pv) || pv > 1) {
+            failed_ = true;
+            return false;
+        }
+        p = pv != 0;
+        return true;
+    }
+};
 
 class EventFile {
 public:
@@ -13,23 +115,22 @@ public:
     // Event(row = file y, column = file x, t)
     template <class T> static void from_file(T *events, std::string fname) {
         std::cout << "Reading from file... (" << fname << ")" << std::endl << std::flush;
-        std::ifstream in(fname, std::ifstream::in);
+        TextEventReader in(fname);
         ull cnt = 0;
         double t = 0, t_0 = 0;
         uint x = 0, y = 0;
         bool p = false;
         clock_t begin = std::clock();
-        if (in >> t_0 >> x >> y >> p) {
+        if (in.next(t_0, x, y, p)) {
             events->push_back(Event(y, x, FROM_SEC(0)));
             cnt++;
         }
-        while (in >> t >> x >> y >> p) {
+        while (in.next(t, x, y, p)) {
             t -= t_0;
             events->push_back(Event(y, x, FROM_SEC(t)));
             cnt++;
         }
         clock_t end = std::clock();
-        in.close();
         if (cnt == 0) {
             std::cout << "Read " << cnt << " events, finished" << std::endl << std::endl << std::flush;
             return;

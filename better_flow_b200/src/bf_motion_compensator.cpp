@@ -176,24 +176,23 @@ int main(int argc, char *argv[]) {
         std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;
     } else {
         std::cout << "Reading from file... (" << file << ")" << std::endl << std::flush;
-        std::ifstream event_file(file, std::ifstream::in);
+        TextEventReader event_file(file);   // block reader + from_chars, same values as `ifstream >>`
         ull i = 0;
         double t = 0;
         uint x = 0, y = 0;
         bool p = false;
         double t_0 = 0;   // the earliest timestamp in the file
-        if (event_file >> t_0 >> x >> y >> p) {
+        if (event_file.next(t_0, x, y, p)) {
             ++i;
             Event e(y, x, FROM_SEC(0));
             estimator.add_event(e);
         }
-        while (event_file >> t >> x >> y >> p) {
+        while (event_file.next(t, x, y, p)) {
             t -= t_0;
             ++i;
             Event e(y, x, FROM_SEC(t));
             estimator.add_event(e);
         }
-        event_file.close();
         std::cout << "Read and processed " << i << " events" << std::endl << std::flush;
     }
 

@@ -1,0 +1,114 @@
+"""Text event reader: better_flow/event_file.h's block reader must yield exactly what the
+reference's `ifstream >> t >> x >> y >> p` loop yields (bf_motion_compensator.cpp:190-202) -- same
+doubles, same stopping point -- only faster."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from better_flow_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def rd():
+    so = os.path.join(HERE, "cpu", "libreader_shim.so")
+    src = os.path.join(HERE, "cpu", "reader_shim.cpp")
+    inc = os.path.join(ROOT, "better_flow_b200", "include")
+    hdrs = [os.path.join(inc, "better_flow", f) for f in os.listdir(os.path.join(inc, "better_flow"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + inc,
+                               "-I" + os.path.join(ROOT, "include"), src, "-o", so])
+    lib = C.CDLL(so)
+    for f in (lib.rd_fast, lib.rd_iostream, lib.rd_from_file):
+        f.restype = C.c_longlong
+    return lib
+
+
+def parse(lib, fn, path, cap):
+    t = np.zeros(cap, np.float64); x = np.zeros(cap, np.uint32); y = np.zeros(cap, np.uint32); p = np.zeros(cap, np.uint8)
+    secs = C.c_double()
+    n = fn(str(path).encode(), C.c_longlong(cap), t.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
+           y.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.byref(secs))
+    return n, t[:n], x[:n], y[:n], p[:n], secs.value
+
+
+def same(a, b):
+    assert a[0] == b[0]
+    assert a[1].tobytes() == b[1].tobytes()      # bit-identical doubles
+    for u, v in zip(a[2:5], b[2:5]):
+        assert np.array_equal(u, v)
+
+
+def test_reader_equals_iostream_on_a_synthetic_stream(rd, tmp_path):
+    st = synth.make_stream(240, 180, 3e6, 0.1, seed=11)
+    path = tmp_path / "ev.txt"
+    st.to_text(str(path))
+    cap = len(st) + 10
+    a = parse(rd, rd.rd_fast, path, cap)
+    b = parse(rd, rd.rd_iostream, path, cap)
+    assert a[0] == len(st)
+    same(a, b)
+    print("parse %d events: block reader %.3f s, iostream %.3f s (%.1fx)" % (a[0], a[5], b[5], b[5] / a[5]))
+    assert a[5] < b[5]
+
+
+@pytest.mark.parametrize("text,expect", [
+    ("", 0),
+    ("\n\n", 0),
+    ("1.5 3 4 1", 1),                                             # no trailing newline
+    ("1.5 3 4 1\n2.5 5 6 0\n", 2),
+    ("  1.5\t3   4 1 \r\n2.5 5 6 0", 2),                          # mixed whitespace, CRLF
+    ("1.5 3\n4 1 2.5\n5 6 0\n", 2),                               # records spanning lines (operator>> does not care)
+    ("1e-3 3 4 1\n+2.5E0 +5 6 0\n.5 1 2 1\n7. 1 2 0\n", 4),        # exponent forms, leading '+', bare dot forms
+    ("1.5 3 4 1\n2.5 5 6 2\n3.5 1 1 1\n", 1),                     # p = 2 is not a bool: stop there
+    ("1.5 3 4 1\nabc 5 6 0\n3.5 1 1 1\n", 1),                     # garbage: stop there
+    ("1.5 3 4 1\n2.5 -5 6 0\n", 2),                               # negative coordinate wraps like strtoul
+    ("1.5 3 4 1\n2.5 5 6\n", 1),                                  # truncated last record
+    ("0.000000001 0 0 0\n1234567890.123456789 239 179 1\n", 2),
+    ("1.5 3 4 1\n2.5 99999999999 6 0\n", 1),                      # coordinate overflows uint
+])
+def test_reader_edge_cases_equal_iostream(rd, tmp_path, text, expect):
+    path = tmp_path / "e.txt"
+    path.write_text(text)
+    a = parse(rd, rd.rd_fast, path, 16)
+    b = parse(rd, rd.rd_iostream, path, 16)
+    assert b[0] == expect, "iostream baseline changed its mind"
+    same(a, b)
+
+
+def test_reader_long_lines_and_block_boundaries(rd, tmp_path):
+    # records separated by long runs of blanks so that tokens straddle the 4 MiB block boundary
+    rng = np.random.default_rng(5)
+    parts = []
+    for i in range(3000):
+        parts.append("%.9f%s%d %d %d%s" % (1.0 + i * 1e-4, " " * int(rng.integers(1, 4000)), rng.integers(0, 240),
+                                           rng.integers(0, 180), rng.integers(0, 2), "\n" if i % 7 else " "))
+    path = tmp_path / "long.txt"
+    path.write_text("".join(parts))
+    a = parse(rd, rd.rd_fast, path, 4000)
+    b = parse(rd, rd.rd_iostream, path, 4000)
+    assert b[0] == 3000
+    same(a, b)
+
+
+def test_missing_file_yields_nothing(rd, tmp_path):
+    a = parse(rd, rd.rd_fast, tmp_path / "nope.txt", 4)
+    assert a[0] == 0
+
+
+def test_from_file_rebases_time_and_swaps_xy(rd, tmp_path):
+    path = tmp_path / "e.txt"
+    path.write_text("10.5 7 3 1\n10.500001 8 4 0\n10.75 9 5 1\n")
+    ts = np.zeros(8, np.uint64); fx = np.zeros(8, np.uint32); fy = np.zeros(8, np.uint32)
+    n = rd.rd_from_file(str(path).encode(), C.c_longlong(8), ts.ctypes.data_as(C.c_void_p), fx.ctypes.data_as(C.c_void_p),
+                        fy.ctypes.data_as(C.c_void_p))
+    assert n == 3
+    # Event(row = file y, column = file x, FROM_SEC(t - t0)) with FROM_SEC(x) = ull(1e9 * x)
+    want = [0, int(1000000000 * (10.500001 - 10.5)), int(1000000000 * (10.75 - 10.5))]
+    assert ts[:3].tolist() == want
+    assert fx[:3].tolist() == [3, 4, 5] and fy[:3].tolist() == [7, 8, 9]
