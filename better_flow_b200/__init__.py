@@ -59,6 +59,9 @@ ABI_SYMBOLS = (
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
     "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile", "bf_model_from_image",
     "bf_batch_run_streamed",
+    "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
+    "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
+    "bf_multi_locate", "bf_multi_launch_count",
 )
 
 _lib = None
@@ -113,6 +116,19 @@ def load() -> C.CDLL:
         lib.bf_project.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_double, C.c_double]
+        lib.bf_multi_create.restype = C.c_void_p
+        lib.bf_multi_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]
+        for name in ("bf_multi_destroy", "bf_multi_device_count", "bf_multi_reset", "bf_multi_sync", "bf_multi_size"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.bf_multi_destroy.restype = None
+        lib.bf_multi_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+        lib.bf_multi_owner.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.bf_multi_add_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.bf_multi_run.argtypes = [C.c_void_p, C.c_int]
+        lib.bf_multi_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(SliceResult)]
+        lib.bf_multi_locate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.bf_multi_launch_count.argtypes = [C.c_void_p]
+        lib.bf_multi_launch_count.restype = C.c_longlong
         assert C.sizeof(SliceResult) == RESULT_BYTES and C.sizeof(Model) == 88
         _lib = lib
     return _lib
@@ -323,3 +339,83 @@ class Context:
         self._chk(self.lib.bf_project(self.h, len(fx), _ptr(fx), _ptr(fy), _ptr(t), _ptr(px), _ptr(py), _ptr(nx),
                                       _ptr(ny), dnx, dny, cx, cy, div, crl))
         return px, py, nx, ny
+
+
+def _result_dict(r: SliceResult) -> dict:
+    return {
+        "rc": r.rc, "iters": r.iters, "model": r.model.as_array(),
+        "dividers": np.array(list(r.dividers), dtype=np.float32),
+        "x_min": r.x_min, "x_max": r.x_max, "y_min": r.y_min, "y_max": r.y_max,
+        "img_rows": r.img_rows, "img_cols": r.img_cols, "x_shift": r.x_shift, "y_shift": r.y_shift,
+        "n_events": r.n_events, "flags": r.flags,
+    }
+
+
+class MultiContext:
+    """bf_multi: one host process, N devices, slices dealt block-cyclically, one NCCL all-gather of the
+    per-slice result records per batch (include/bf_cuda.h)."""
+
+    def __init__(self, n_devices, sensor_rows=180, sensor_cols=240, max_scale=3, max_events_per_device=1 << 20,
+                 max_slices_per_device=64, devices=None):
+        self.lib = load()
+        dev = (C.c_int * n_devices)(*devices) if devices is not None else None
+        self.h = self.lib.bf_multi_create(n_devices, dev, sensor_rows, sensor_cols, max_scale,
+                                          int(max_events_per_device), int(max_slices_per_device))
+        if not self.h:
+            raise BfError(self.lib.bf_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bf_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise BfError(self.lib.bf_last_error().decode())
+        return rc
+
+    @property
+    def n_devices(self):
+        return int(self.lib.bf_multi_device_count(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.bf_multi_launch_count(self.h))
+
+    def set_option(self, key, value):
+        self._chk(self.lib.bf_multi_set_option(self.h, key.encode(), int(value)))
+
+    def reset(self):
+        self._chk(self.lib.bf_multi_reset(self.h))
+
+    def add_packed(self, events, scale=3, max_iter=-1):
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        return self._chk(self.lib.bf_multi_add_packed(self.h, _ptr(ev), len(ev), scale, max_iter))
+
+    def run(self, want_events=False):
+        self._chk(self.lib.bf_multi_run(self.h, 1 if want_events else 0))
+
+    def sync(self):
+        self._chk(self.lib.bf_multi_sync(self.h))
+
+    def size(self):
+        return int(self.lib.bf_multi_size(self.h))
+
+    def result(self, k) -> dict:
+        r = SliceResult()
+        self._chk(self.lib.bf_multi_result(self.h, k, C.byref(r)))
+        return _result_dict(r)
+
+    def results(self):
+        return [self.result(k) for k in range(self.size())]
+
+    def locate(self, k):
+        ctx, slot, dev = C.c_void_p(0), C.c_int(0), C.c_int(0)
+        self._chk(self.lib.bf_multi_locate(self.h, k, C.byref(ctx), C.byref(slot), C.byref(dev)))
+        return int(slot.value), int(dev.value)

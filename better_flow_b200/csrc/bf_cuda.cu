@@ -416,6 +416,9 @@ static int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+// used by bf_multi.cpp (same shared object) to report through bf_last_error()
+extern "C" void bf_set_error_(const char *msg) { g_err = msg ? msg : ""; }
+
 #define CU(call)                                                                                 \
     do {                                                                                         \
         cudaError_t e_ = (call);                                                                 \
@@ -736,12 +739,6 @@ static int add_desc(bf_ctx *c, long long off, int n, int scale, int max_iter, co
     if (init) d.init = *init;
     c->uploaded = c->ran = false;
     return c->n_slices++;
-}
-
-static int check_coords(bf_ctx *c, unsigned fx, unsigned fy) {
-    if (fx >= (unsigned)c->res_x || fy >= (unsigned)c->res_y)
-        return fail(BF_ERR_ARG, "event (%u,%u) outside the %dx%d sensor", fx, fy, c->res_x, c->res_y);
-    return BF_OK;
 }
 
 int bf_batch_add(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,

@@ -7,12 +7,15 @@
 //   * run-time buffer capacity / time span (the template arguments stay the defaults),
 //   * set_batch(n): with stm disabled slices are independent, so n of them are queued and minimised
 //     by ONE persistent-kernel launch (bf_batch_*),
+//   * set_gpus(n): the queued batch is dealt to n devices (bf_multi_*: one launch per device, one
+//     NCCL all-gather of the per-slice flow records),
 //   * set_flow_out(stream): one machine-readable line per slice,
 //   * set_quiet(): suppress the reference's per-slice dump of every past model.
 // Video / picture generation and the interactive mode are GUI features and are accepted but ignored.
 #ifndef BF_DVS_FLOW_H
 #define BF_DVS_FLOW_H
 
+#include <algorithm>
 #include <map>
 
 #include <better_flow/common.h>
@@ -52,6 +55,7 @@ protected:
     };
     std::vector<Pending> pending_;
     int batch_;
+    int gpus_;
     bool quiet_;
     std::ostream *flow_out_;
     ull slices_done_;
@@ -62,14 +66,14 @@ public:
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time = 0)
         : on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
-          scale(3), stm_disable(false), batch_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          scale(3), stm_disable(false), batch_(1), gpus_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
           iters_done_(0) {}
 
     // run-time sized variant (CLI flags --max-events / --slice-time)
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time, size_t capacity, sll span)
         : ev_buffer(capacity, span), on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
-          scale(3), stm_disable(false), batch_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          scale(3), stm_disable(false), batch_(1), gpus_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
           iters_done_(0) {}
 
     ~DVS_flow() {}
@@ -100,6 +104,7 @@ public:
 
     // extensions
     void set_batch(int n) { batch_ = n < 1 ? 1 : n; }
+    void set_gpus(int n) { gpus_ = n < 1 ? 1 : n; }
     void set_quiet(bool q = true) { quiet_ = q; }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
     ObjectModel get_last_model() { return last_model; }
@@ -209,23 +214,51 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
     if (pending_.empty()) return;
-    long long total = 0;
-    for (auto &p : pending_) total += (long long)p.packed.size();
-    bf_ctx *ctx = CudaDriver::context(total, (int)pending_.size(), scale);
     auto check = [](int rc, const char *what) {
         if (rc < 0) {
             std::cerr << what << " failed: " << bf_last_error() << std::endl;
             std::exit(1);
         }
     };
-    check(bf_batch_reset(ctx), "bf_batch_reset");
-    for (auto &p : pending_) check(bf_batch_add_packed(ctx, p.packed.data(), (int)p.packed.size(), scale, max_iter, nullptr), "bf_batch_add_packed");
-    check(bf_batch_run(ctx, accumulate ? 1 : 0), "bf_batch_run");
+    const int n_pending = (int)pending_.size();
+    bf_ctx *ctx = nullptr;
+    bf_multi *multi = nullptr;
+    if (gpus_ > 1) {
+        // capacity per device = the largest share the block-cyclic deal can produce
+        const int block = 4;
+        std::vector<long long> ev((size_t)gpus_, 0);
+        std::vector<int> sl((size_t)gpus_, 0);
+        for (int k = 0; k < n_pending; ++k) {
+            const int o = bf_multi_owner(k, gpus_, block);
+            ev[(size_t)o] += (long long)pending_[(size_t)k].packed.size();
+            sl[(size_t)o] += 1;
+        }
+        multi = CudaDriver::multi(gpus_, *std::max_element(ev.begin(), ev.end()), *std::max_element(sl.begin(), sl.end()), scale);
+        check(bf_multi_reset(multi), "bf_multi_reset");
+        check(bf_multi_set_option(multi, "block", block), "bf_multi_set_option");
+        for (auto &p : pending_) check(bf_multi_add_packed(multi, p.packed.data(), (int)p.packed.size(), scale, max_iter), "bf_multi_add_packed");
+        check(bf_multi_run(multi, accumulate ? 1 : 0), "bf_multi_run");
+        check(bf_multi_sync(multi), "bf_multi_sync");
+    } else {
+        long long total = 0;
+        for (auto &p : pending_) total += (long long)p.packed.size();
+        ctx = CudaDriver::context(total, n_pending, scale);
+        check(bf_batch_reset(ctx), "bf_batch_reset");
+        for (auto &p : pending_) check(bf_batch_add_packed(ctx, p.packed.data(), (int)p.packed.size(), scale, max_iter, nullptr), "bf_batch_add_packed");
+        check(bf_batch_run(ctx, accumulate ? 1 : 0), "bf_batch_run");
+    }
     std::vector<double> nx, ny, px, py;
     for (size_t k = 0; k < pending_.size(); ++k) {
         Pending &p = pending_[k];
         bf_slice_result r;
-        check(bf_batch_result(ctx, (int)k, &r), "bf_batch_result");
+        bf_ctx *ev_ctx = ctx;
+        int ev_slot = (int)k;
+        if (multi) {
+            check(bf_multi_result(multi, (int)k, &r), "bf_multi_result");
+            check(bf_multi_locate(multi, (int)k, &ev_ctx, &ev_slot, nullptr), "bf_multi_locate");
+        } else {
+            check(bf_batch_result(ctx, (int)k, &r), "bf_batch_result");
+        }
         p.log.model.from_pod(r.model);
         log_slice(p.log, r.iters, r.rc);
         if (accumulate) {
@@ -233,7 +266,7 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
             // buffer is full; the packed slice is newest -> oldest.  Map by walking backwards.
             const size_t n = p.packed.size();
             nx.resize(n); ny.resize(n); px.resize(n); py.resize(n);
-            check(bf_batch_events(ctx, (int)k, px.data(), py.data(), nx.data(), ny.data()), "bf_batch_events");
+            check(bf_batch_events(ev_ctx, ev_slot, px.data(), py.data(), nx.data(), ny.data()), "bf_batch_events");
             const size_t m = p.copy.size();
             for (size_t i = 0; i < m; ++i) {
                 Event &e = p.copy[i];

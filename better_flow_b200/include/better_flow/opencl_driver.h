@@ -53,10 +53,35 @@ public:
         return s.ctx;
     }
 
+    // Pooled multi-GPU front (bf_multi_*): `gpus` devices starting at the selected one.
+    static bf_multi *multi(int gpus, long long need_events_per_dev, int need_slices_per_dev, int need_scale) {
+        if (!enabled_ref()) init(device_ref());
+        State &s = state();
+        const bool fits = s.multi && s.m_gpus == gpus && s.m_rows == RES_X && s.m_cols == RES_Y &&
+                          need_events_per_dev <= s.m_events && need_slices_per_dev <= s.m_slices && need_scale <= s.m_scale;
+        if (!fits) {
+            if (s.multi) bf_multi_destroy(s.multi);
+            s.m_gpus = gpus; s.m_rows = RES_X; s.m_cols = RES_Y;
+            s.m_events = std::max<long long>(need_events_per_dev + need_events_per_dev / 4, 1 << 16);
+            s.m_slices = std::max(need_slices_per_dev, 16);
+            s.m_scale = std::max(need_scale, s.m_scale);
+            std::vector<int> ids;
+            for (int i = 0; i < gpus; ++i) ids.push_back(device_ref() + i);
+            s.multi = bf_multi_create(gpus, ids.data(), s.m_rows, s.m_cols, s.m_scale, s.m_events, s.m_slices);
+            if (!s.multi) {
+                std::cerr << "bf_multi_create failed: " << bf_last_error() << std::endl;
+                std::exit(1);
+            }
+        }
+        return s.multi;
+    }
+
     static void shutdown() {
         State &s = state();
         if (s.ctx) bf_ctx_destroy(s.ctx);
         s.ctx = nullptr;
+        if (s.multi) bf_multi_destroy(s.multi);
+        s.multi = nullptr;
     }
 
 private:
@@ -64,6 +89,9 @@ private:
         bf_ctx *ctx = nullptr;
         int rows = 0, cols = 0, slices = 0, scale = 3;
         long long events = 0;
+        bf_multi *multi = nullptr;
+        int m_gpus = 0, m_rows = 0, m_cols = 0, m_slices = 0, m_scale = 3;
+        long long m_events = 0;
     };
     static State &state() {
         static State s;

@@ -35,6 +35,7 @@ static long long max_events = EVENT_WIDTH;
 static int sensor_w = 240, sensor_h = 180;
 static char *flowOutName = NULL;
 static int batch = 1;
+static int gpus = 1;
 static int device = 0;
 
 static void lPrintVersion() {
@@ -70,6 +71,8 @@ static void usage(int ret) {
     printf("    [--sensor=WxH]\t\t\tSensor size in pixels (default = %ix%i)\n", sensor_w, sensor_h);
     printf("    [--flow-out=<name>]\t\t\tWrite one line per slice: id n iters rc total_dx total_dy total_rot total_div cx cy dx dy rot div cnt\n");
     printf("    [--batch=N]\t\t\t\tWith --stm-disable: minimise N slices per kernel launch (default = %i)\n", batch);
+    printf("    [--gpus=N]\t\t\t\tWith --stm-disable and --batch: deal every batch to N devices (starting at --device),\n");
+    printf("              \t\t\t\tone launch per device and one NCCL all-gather of the per-slice flow (default = %i)\n", gpus);
     printf("    [--device=N]\t\t\tCUDA device (default = %i)\n", device);
     printf("    <file to process or \"-\" for stdin>\n");
     exit(ret);
@@ -112,6 +115,7 @@ int main(int argc, char *argv[]) {
         }
         else if (!strncmp(argv[i], "--flow-out=", 11)) flowOutName = argv[i] + 11;
         else if (!strncmp(argv[i], "--batch=", 8)) batch = atoi(argv[i] + 8);
+        else if (!strncmp(argv[i], "--gpus=", 7)) gpus = atoi(argv[i] + 7);
         else if (!strncmp(argv[i], "--device=", 9)) device = atoi(argv[i] + 9);
         else if (!strcmp(argv[i], "-")) {}
         else if (argv[i][0] == '-') { fprintf(stderr, "Unknown option \"%s\".\n", argv[i]); usage(1); }
@@ -126,6 +130,8 @@ int main(int argc, char *argv[]) {
     if (file == NULL) { fprintf(stderr, "No input file.\n"); usage(1); }
     if (scale != 1 && scale != 3 && scale != 5) { fprintf(stderr, "--scale must be 1, 3 or 5.\n"); return 1; }
     if (batch > 1 && !stm_disable) { fprintf(stderr, "--batch needs --stm-disable (warm-started slices form a chain).\n"); return 1; }
+    if (gpus > 1 && !stm_disable) { fprintf(stderr, "--gpus needs --stm-disable (warm-started slices form a chain).\n"); return 1; }
+    if (gpus > 1 && batch < gpus) { fprintf(stderr, "--gpus=%d needs --batch of at least %d slices.\n", gpus, gpus); return 1; }
     (void)gpu; (void)img; (void)video;
 
     bf::set_sensor(sensor_h, sensor_w);   // RES_X = rows, RES_Y = columns
@@ -141,6 +147,7 @@ int main(int argc, char *argv[]) {
     estimator.set_max_iter(max_iter);
     estimator.set_scale(scale);
     estimator.set_batch(batch);
+    estimator.set_gpus(gpus);
     estimator.set_quiet(quiet);
     std::ofstream flow_out;
     if (flowOutName != NULL) {

@@ -197,6 +197,38 @@ int bf_project(bf_ctx *ctx, int n, const uint16_t *fr_x, const uint16_t *fr_y, c
                double *pr_x, double *pr_y, double *nx, double *ny,
                double dnx, double dny, double cx, double cy, double div, double crl);
 
+/* ---- slice-sharded multi-GPU front ----------------------------------------------
+ * The reference has no multi-device path at all (one OpenCL queue on platform[0]/device[0],
+ * src/opencl_driver.cpp:25-39).  Slices are independent under --stm-disable semantics
+ * (dvs_flow.h:218-219), so a batch is dealt to N devices in blocks of `block` consecutive slices
+ * (option "block", default 4), every device minimises its share with its own persistent launch, and
+ * the per-slice result records are exchanged with ONE ncclAllGather per batch.  One host process
+ * drives all devices (ncclCommInitAll); NCCL is loaded with dlopen when n_devices > 1.
+ * Warm-started chains cannot be sharded: init models are not accepted here. */
+typedef struct bf_multi bf_multi;
+
+/* devices == NULL means 0..n_devices-1.  Capacities are per device. */
+bf_multi *bf_multi_create(int n_devices, const int *devices, int sensor_rows, int sensor_cols, int max_scale,
+                          long long max_events_per_device, int max_slices_per_device);
+void bf_multi_destroy(bf_multi *m);
+int bf_multi_device_count(bf_multi *m);
+/* "block", or any bf_ctx_set_option key (applied to every device's context). */
+int bf_multi_set_option(bf_multi *m, const char *key, long long value);
+/* Owner device index of global slice k: (k / block) % n_devices. */
+int bf_multi_owner(int slice, int n_devices, int block);
+
+int bf_multi_reset(bf_multi *m);
+/* Appends the next slice (global index = call order); returns that index. */
+int bf_multi_add_packed(bf_multi *m, const bf_event *events, int n, int scale, int max_iter);
+/* H2D + launch on every device, the all-gather, D2H of the gathered records.  Asynchronous. */
+int bf_multi_run(bf_multi *m, int want_events);
+int bf_multi_sync(bf_multi *m);
+int bf_multi_size(bf_multi *m);
+int bf_multi_result(bf_multi *m, int slice, bf_slice_result *out);
+/* Context / slot / CUDA device a slice was minimised on (per-event read-back via bf_batch_events). */
+int bf_multi_locate(bf_multi *m, int slice, bf_ctx **ctx, int *slot, int *device);
+long long bf_multi_launch_count(bf_multi *m);
+
 #ifdef __cplusplus
 }
 #endif

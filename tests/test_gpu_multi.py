@@ -1,0 +1,102 @@
+"""bf_multi_* (include/bf_cuda.h): the slice-sharded multi-GPU front -- block-cyclic deal of a batch,
+one persistent launch per device, ONE NCCL all-gather of the per-slice flow records.
+Results must be identical to the single-context batch, whatever the device count."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import better_flow_b200 as bf
+from better_flow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "better_flow_b200", "bf_motion_compensator")
+
+
+def batch():
+    st = synth.make_stream(240, 180, 2.0e6, 0.26, seed=23)
+    return synth.cut_slices(st, 0.02)[:13]
+
+
+def single(slices, ctx240):
+    ctx240.reset()
+    for s in slices:
+        ctx240.add(s.fr_x, s.fr_y, s.t_ns, 3, 12)
+    ctx240.run()
+    return ctx240.results()
+
+
+def same_results(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x["rc"] == y["rc"] and x["iters"] == y["iters"] and x["n_events"] == y["n_events"]
+        assert x["model"].tobytes() == y["model"].tobytes()
+        assert x["dividers"].tobytes() == y["dividers"].tobytes()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_multi_equals_single_context(ctx240, n_dev):
+    if bf.load().bf_device_count() < n_dev:
+        pytest.skip("needs %d CUDA devices" % n_dev)
+    slices = batch()
+    want = single(slices, ctx240)
+    m = bf.MultiContext(n_dev, 180, 240, 3, max_events_per_device=1 << 20, max_slices_per_device=16)
+    try:
+        for rep in range(2):                      # the context is reusable
+            m.reset()
+            for s in slices:
+                m.add_packed(bf.pack_events(s.fr_x, s.fr_y, s.t_ns), 3, 12)
+            m.run()
+            m.sync()
+            same_results(m.results(), want)
+        owners = [m.locate(k)[1] for k in range(len(slices))]
+        assert owners == [(k // 4) % n_dev for k in range(len(slices))]
+        assert m.launches == 2 * min(n_dev, (len(slices) + 3) // 4)
+    finally:
+        m.close()
+
+
+def test_multi_ragged_batches(ctx240):
+    """Fewer slices than devices x block, an empty batch, and a slice below the 1000-event guard."""
+    n_dev = min(2, bf.load().bf_device_count())
+    slices = batch()[:3]
+    m = bf.MultiContext(n_dev, 180, 240, 3, max_events_per_device=1 << 20, max_slices_per_device=16)
+    try:
+        m.set_option("block", 1)
+        m.reset(); m.run(); m.sync()
+        assert m.size() == 0
+        m.reset()
+        for s in slices:
+            m.add_packed(bf.pack_events(s.fr_x, s.fr_y, s.t_ns), 3, 12)
+        tiny = slices[0]
+        m.add_packed(bf.pack_events(tiny.fr_x[:500], tiny.fr_y[:500], tiny.t_ns[:500]), 3, 12)
+        m.run(); m.sync()
+        got = m.results()
+        same_results(got[:3], single(slices, ctx240))
+        assert got[3]["rc"] == bf.RC_SKIPPED and got[3]["n_events"] == 500
+    finally:
+        m.close()
+
+
+def test_cli_gpus_flag_equals_single_gpu(tmp_path):
+    if bf.load().bf_device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "better_flow_b200"), "cli"])
+    st = synth.make_stream(240, 180, 2.0e6, 0.2, seed=29)
+    rec = np.zeros(len(st), dtype=np.dtype([("t", "<u8"), ("x", "<u2"), ("y", "<u2"), ("p", "<u4")]))
+    rec["t"], rec["x"], rec["y"], rec["p"] = st.t_ns, st.x, st.y, st.p
+    binf = tmp_path / "s.bin"
+    rec.tofile(binf)
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("f%d.txt" % gpus)
+        r = subprocess.run([CLI, "--quiet", "--stm-disable", "--max-iter=10", "--batch=6", "--gpus=%d" % gpus,
+                            "--flow-out=%s" % out, "-o", str(tmp_path / ("uv%d.txt" % gpus)), str(binf)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append((open(out).read(), open(tmp_path / ("uv%d.txt" % gpus)).read()))
+    assert outs[0] == outs[1] and len(outs[0][0].splitlines()) >= 8

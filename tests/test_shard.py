@@ -70,3 +70,26 @@ def test_two_rank_gloo_shard_and_gather(oracle_port):
         assert list(rec[:, 0].astype(int)) == list(range(len(slices)))
         assert np.array_equal(rec[:, 5:16], want)
         assert np.all(rec[:, 2] == 5)
+
+
+def test_native_owner_rule_equals_python_partition():
+    """bf_multi_owner (C ABI, used by the C++ front end's --gpus) deals slices exactly like shard.partition."""
+    import better_flow_b200 as bf
+    lib = bf.load()
+    for n in (1, 7, 64, 297):
+        for world in (1, 2, 4, 8):
+            for block in (1, 4, 5):
+                owners = [lib.bf_multi_owner(k, world, block) for k in range(n)]
+                for r in range(world):
+                    assert [k for k, o in enumerate(owners) if o == r] == shard.partition(n, world, r, block)
+    assert lib.bf_multi_owner(-1, 2, 4) == -1 and lib.bf_multi_owner(3, 0, 4) == -1
+
+
+def test_multi_front_fails_loudly_without_devices():
+    import better_flow_b200 as bf
+    lib = bf.load()
+    if lib.bf_device_count() >= 2:
+        pytest.skip("two CUDA devices are present")
+    with pytest.raises(bf.BfError) as e:
+        bf.MultiContext(2, 180, 240, 3, 1 << 16, 8)
+    assert "no CPU fallback" in str(e.value)
