@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbf_cuda.so")
+# BF_LIB_PATH: development aid for same-box A/B runs of two builds of the library (tools/ab_libs.py)
+LIB_PATH = os.environ.get("BF_LIB_PATH") or os.path.join(HERE, "libbf_cuda.so")
 
 RESULT_BYTES = 160  # sizeof(bf_slice_result), checked in load()
 RC_OK, RC_SKIPPED, RC_ITER_CAP, RC_DEGENERATE = 0, 1, 2, 3

@@ -25,6 +25,7 @@ struct __align__(16) Smem {
     double red[BF_NW * BF_NSUMS];
     unsigned short list[2][BF_LIST_CAP];   // live cells of this iteration / of the previous one
     int scan[BF_NW];
+    float2 rcp_tab[BF_RCP_TAB];            // (c, RN(1/c)) for the fast unpack
     SliceDesc sd;
     BfGeom g;
     BfPack pk;
@@ -45,6 +46,10 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
     const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
 
+    // per-slice cell tables live behind the fixed part of the shared-memory block
+    int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
+    short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
+    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
     if (threadIdx.x == 0) {
         bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
         if (S.sd.has_init) {
@@ -73,7 +78,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
         event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new, nullptr,
-                       flags_new, tag);
+                       flags_new, tag, row_tab, col_tab);
         if (pf) __syncthreads();
         PF_MARK(PF_EVENT);
         {
@@ -84,7 +89,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
 
         Acc acc;
         acc_zero(acc);
-        n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, flags_new, tag, rank, P.G, S.list[buf], S.scan,
+        n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, P.G, S.list[buf], S.scan,
                                        nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
                                        n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
         if (pf) __syncthreads();
@@ -114,14 +119,14 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     // slice's first splat comes two group barriers later).
     {
         Acc none;
-        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, nullptr, 0u, rank, P.G, S.list[buf ^ 1], S.scan, nullptr,
+        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, S.rcp_tab, nullptr, 0u, rank, P.G, S.list[buf ^ 1], S.scan, nullptr,
                               nullptr, nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag,
                               n_prev >= 0 ? S.list[buf] : nullptr, n_prev);
     }
     // Last re-projection of iteration_step (optimizer_rolling.h:340-344): only needed when the caller
     // wants the per-event state back (writeout_events).
     if (P.want_events)
-        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, true, nullptr, P.nxy, nullptr, 0u);
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
     if (pf) __syncthreads();
     PF_MARK(PF_FINAL);
     if (prof) pf[PF_SLICES] += 1;
@@ -142,6 +147,7 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
     int parity = 0;
     long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
     const long long t_begin = pf ? clock64() : 0;
+    fill_rcp_table(S.rcp_tab);   // made visible by the first group barrier's __syncthreads
 
     for (;;) {
         const long long t_pro = pf ? clock64() : 0;
@@ -239,11 +245,11 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
                 bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
             }
             __syncthreads();
-            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, P.nxy, nullptr, 0u);
+            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
         } else if (guard != 0 && P.want_events) {
             BfProj none;
             none.dnx = none.dny = none.cx = none.cy = none.div = none.s = 0; none.c = 1;
-            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, P.nxy, nullptr, 0u);
+            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
         }
         __syncthreads();
 
@@ -309,7 +315,9 @@ __global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StagePar
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     Acc acc;
     acc_zero(acc);
-    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, P.flags, P.tag, blockIdx.x, gridDim.x, S.list[0], S.scan,
+    fill_rcp_table(S.rcp_tab);
+    __syncthreads();
+    image_pass<SH, true>(acc, P.img, P.pitch, P.g, P.pk, S.rcp_tab, P.flags, P.tag, blockIdx.x, gridDim.x, S.list[0], S.scan,
                          P.out_img, P.out_gx, P.out_gy, nullptr, nullptr, 0u, nullptr, -1);
     acc_block_reduce(acc, S.red, P.partials + blockIdx.x * BF_NSUMS);
 }
@@ -392,7 +400,7 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double px = pr_x[i], py = pr_y[i], ex, ey;
         float mx, my;
-        project_event(px, py, ex, ey, mx, my, (float)fr_x[i], (float)fr_y[i], (float)t[i], q);
+        project_event(px, py, ex, ey, mx, my, (double)fr_x[i], (double)fr_y[i], (float)t[i], q);
         pr_x[i] = px; pr_y[i] = py;
         if (nx) nx[i] = ex;
         if (ny) ny[i] = ey;
@@ -490,6 +498,10 @@ struct bf_ctx {
 };
 
 static size_t smem_bytes() { return sizeof(Smem); }
+// minimise kernel: fixed block + the per-slice cell tables (int2 per image row, short2 per image column)
+static size_t smem_bytes_min(const bf_ctx *c) {
+    return sizeof(Smem) + (size_t)c->max_scale * c->res_x * sizeof(int2) + (size_t)c->max_scale * c->res_y * sizeof(short2);
+}
 
 static int ensure_device() {
     if (g_device < 0) {
@@ -561,7 +573,7 @@ static int configure(bf_ctx *c, int n_slices) {
         c->ctrl_bytes = 256 + (size_t)want * sizeof(GroupWs);
         CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
         // one partial record per CTA slot, whatever the grouping
-        CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 2 * BF_NSUMS * sizeof(double)));
+        CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 4 * BF_NSUMS * sizeof(double)));
     }
     pick_launch(c, n_slices, &c->G, &c->n_groups);
     return BF_OK;
@@ -634,13 +646,27 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaMallocHost(&c->h_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMallocHost(events)", e);
     if ((e = cudaMallocHost(&c->h_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMallocHost(slices)", e);
     if ((e = cudaMallocHost(&c->h_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMallocHost(results)", e);
-    if ((e = cudaMalloc(&c->d_events, (size_t)max_events * sizeof(bf_event))) != cudaSuccess) return bail("cudaMalloc(events)", e);
-    if ((e = cudaMalloc(&c->d_state, (size_t)max_events * sizeof(float2))) != cudaSuccess) return bail("cudaMalloc(state)", e);
+    // (+2: the event pass reads events / states in aligned pairs, so the pair holding the last event is read whole)
+    if ((e = cudaMalloc(&c->d_events, (size_t)(max_events + 2) * sizeof(bf_event))) != cudaSuccess) return bail("cudaMalloc(events)", e);
+    if ((e = cudaMalloc(&c->d_state, (size_t)(max_events + 2) * sizeof(float2))) != cudaSuccess) return bail("cudaMalloc(state)", e);
     if ((e = cudaMalloc(&c->d_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMalloc(slices)", e);
     if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
 
-    if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
-    if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if (smem_bytes_min(c) > 100 * 1024) {
+        fail(BF_ERR_ARG, "sensor too large for the per-slice cell tables (%zu bytes of shared memory)", smem_bytes_min(c));
+        bf_ctx_destroy(c);
+        return nullptr;
+    }
+    // (the attribute is per function, not per context: only ever raise it)
+    static int smem_attr = 0;
+    if ((int)smem_bytes_min(c) > smem_attr) {
+        smem_attr = (int)smem_bytes_min(c);
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+#if BF_NT <= 256
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+#endif
+    }
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(bf_stage_image_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes())) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
@@ -674,7 +700,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
     else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
-    else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = value >= 2 ? 2 : 1;
+    else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = (value >= 4 && BF_NT <= 256) ? 4 : (value >= 2 ? 2 : 1);
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
     return BF_OK;
 }
@@ -690,7 +716,7 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!strcmp(key, "sms")) return c->sms;
     if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;
     if (!strcmp(key, "image_bytes")) return c->img_elems * 8;
-    if (!strcmp(key, "smem_bytes")) return (long long)smem_bytes();
+    if (!strcmp(key, "smem_bytes")) return (long long)smem_bytes_min(c);
     return -1;
 }
 
@@ -857,6 +883,7 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
     P.ready = ready;
+    P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
     P.prof = nullptr;
     if (c->profile) {
         if (!c->d_prof) CU(cudaMalloc(&c->d_prof, (size_t)1024 * BF_NPROF * sizeof(long long)));
@@ -865,7 +892,10 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     }
     void *args[] = {&P};
     void *kern = c->ctas_per_sm == 2 ? (void *)bf_minimize_kernel<2> : (void *)bf_minimize_kernel<1>;
-    CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes(), c->stream));
+#if BF_NT <= 256
+    if (c->ctas_per_sm == 4) kern = (void *)bf_minimize_kernel<4>;
+#endif
+    CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
     c->launches += 1;
     c->ran = true;
     c->have_events = want_events != 0;

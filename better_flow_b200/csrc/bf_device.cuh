@@ -28,7 +28,9 @@
 #include "bf_logic.h"
 
 // ---- compile-time geometry -------------------------------------------------------------------
+#ifndef BF_NT
 #define BF_NT 512              // threads per CTA (16 warps)
+#endif
 #define BF_NW (BF_NT / 32)
 #ifndef BF_MIN_CTAS
 #define BF_MIN_CTAS 1          // resident CTAs per SM the minimise kernel is compiled for (register cap = 65536 / (BF_NT * this))
@@ -91,6 +93,7 @@ struct KParams {
     int min_events;          // 1000 (optimizer_rolling.h:57)
     int iter_cap;
     int want_events;
+    int tab_rows, tab_cols;  // capacity of the per-slice cell tables in dynamic shared memory (max image rows / cols)
     const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)
     long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
 };
@@ -112,6 +115,11 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_nc_u32x4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {
     uint2 v;
@@ -159,14 +167,18 @@ __device__ __forceinline__ float slope_time(double n, float tf) {
     const float k = (float)div_const((double)(float)n, 127.0, 1.0 / 127.0);
     return __fmul_rn(k, tf);
 }
-__device__ __forceinline__ double warp_from_m(float m, float fr) {
-    return __dsub_rn((double)fr, div_const((double)m, 10000.0, 1.0 / 10000.0));
+__device__ __forceinline__ double warp_from_m(float m, double fr) {
+    return __dsub_rn(fr, div_const((double)m, 10000.0, 1.0 / 10000.0));
+}
+// Exact u32 (< 2^32) -> f64 on the FP64 pipe (2^52 exponent trick) instead of an I2F on the XU pipe.
+__device__ __forceinline__ double u32_to_double(unsigned v) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)v), 4503599627370496.0);
 }
 
 // Event::project_4param_reinit + apply_project (event.h:99-110,164-168) for one event.
 // All FP64 operations individually rounded (no contraction), in the reference's order.
 __device__ __forceinline__ void project_event(double &prx, double &pry, double &ex, double &ey, float &mx, float &my,
-                                              float frx, float fry, float tf, const BfProj &q) {
+                                              double frx, double fry, float tf, const BfProj &q) {
     const double rx = __dsub_rn(prx, q.cx), ry = __dsub_rn(pry, q.cy);                           // :100
     const double qx = __dsub_rn(__dmul_rn(q.c, rx), __dmul_rn(q.s, ry));                        // :102
     const double qy = __dadd_rn(__dmul_rn(q.s, rx), __dmul_rn(q.c, ry));                        // :103
@@ -181,31 +193,29 @@ __device__ __forceinline__ void project_event(double &prx, double &pry, double &
 }
 
 // Pixel of an event in the time image, AccelLib::get_time_img_cpu (accel_lib.h:154-158):
-//   int x = pr_x * scale + x_sh (f64, truncation toward zero), rejected unless half <= x < w + half.
-// The test is done on the f64 value before truncation, which is equivalent for integer bounds
-// (trunc(f) >= k  <=>  f >= k for k >= 1, f > -1 for k == 0;  trunc(f) < k  <=>  f < k for k >= 1)
-// and rejects NaN like x86's cvttsd2si(NaN) = INT_MIN does.
+//   int x = pr_x * scale + x_sh (f64 arithmetic, C truncation toward zero), rejected unless
+//   half <= x < w + half.
+// The test is done on the truncated integers, as the reference does it.  Out-of-range values:
+// x86's cvttsd2si returns INT_MIN for NaN / overflow (rejected by x < half); cvt.rzi.s32.f64
+// saturates to INT_MIN / INT_MAX (both rejected) and maps NaN to 0, which `x < half` rejects too
+// except for half == 0 (scale 1), where NaN is tested explicitly.
 struct PixelMap {
     double sc, xs, ys;       // scale, x_sh, y_sh as f64
-    double xlo, xhi, ylo, yhi;
-    bool lo_open;            // half == 0: lower bound is the open interval (-1, ...)
+    int half, w, h;
     int pitch;
 };
 __device__ __forceinline__ void make_pixel_map(PixelMap &m, const BfGeom &g, int pitch) {
     m.sc = (double)g.scale; m.xs = (double)g.x_sh; m.ys = (double)g.y_sh;
-    m.lo_open = g.half == 0;
-    m.xlo = m.lo_open ? -1.0 : (double)g.half;
-    m.ylo = m.xlo;
-    m.xhi = (double)(g.w + g.half);
-    m.yhi = (double)(g.h + g.half);
+    m.half = g.half; m.w = g.w; m.h = g.h;
     m.pitch = pitch;
 }
 __device__ __forceinline__ bool event_pixel(double prx, double pry, const PixelMap &m, int &x, int &y) {
     const double fx = __dadd_rn(__dmul_rn(prx, m.sc), m.xs);
     const double fy = __dadd_rn(__dmul_rn(pry, m.sc), m.ys);
-    const bool ok = (m.lo_open ? (fx > m.xlo && fy > m.ylo) : (fx >= m.xlo && fy >= m.ylo)) && fx < m.xhi && fy < m.yhi;
-    x = (int)fx;
-    y = (int)fy;
+    x = __double2int_rz(fx);
+    y = __double2int_rz(fy);
+    bool ok = (unsigned)(x - m.half) < (unsigned)m.w && (unsigned)(y - m.half) < (unsigned)m.h;
+    if (m.half == 0) ok = ok && fx == fx && fy == fy;
     return ok;
 }
 __device__ __forceinline__ long long pixel_offset(int x, int y, int pitch) {
@@ -229,6 +239,40 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
     }
 }
 
+// The same stamping with the per-row / per-column parts looked up instead of computed: the cell
+// geometry of a slice is fixed for all its iterations, so every CTA tabulates it once per slice in
+// shared memory (the computed form is ~45 instructions per event, the table form ~12).
+//   row_tab[x] = (first flag index of x's cell row, +-n_cj or 0: offset to the neighbouring cell row to stamp too)
+//   col_tab[y] = (cell column of y, +-1 or 0)
+template <int SH>
+__device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab, int rows, int cols) {
+    typedef CellCfg<SH> C;
+    const int n_ci = (rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (cols + C::CW - 1) / C::CW;
+    for (int x = threadIdx.x; x < rows; x += blockDim.x) {
+        const int ci = x >> 3, lx = x & 7;
+        const int di = (lx < C::H && ci > 0) ? -n_cj : ((lx >= BF_CELL_ROWS - C::H && ci + 1 < n_ci) ? n_cj : 0);
+        row_tab[x] = make_int2(ci * n_cj, di);
+    }
+    for (int y = threadIdx.x; y < cols; y += blockDim.x) {
+        const int cj = y / C::CW, ly = y - cj * C::CW;
+        const int dj = (ly < C::H && cj > 0) ? -1 : ((ly >= C::CW - C::H && cj + 1 < n_cj) ? 1 : 0);
+        col_tab[y] = make_short2((short)cj, (short)dj);
+    }
+}
+__device__ __forceinline__ void mark_cells_tab(unsigned *flags, unsigned tag, int x, int y, const int2 *row_tab,
+                                               const short2 *col_tab) {
+    const int2 r = row_tab[x];
+    const short2 c = col_tab[y];
+    const int f = r.x + (int)c.x;
+    const int dj = (int)c.y;
+    flags[f] = tag;
+    if (dj != 0) flags[f + dj] = tag;
+    if (r.y != 0) {
+        flags[f + r.y] = tag;
+        if (dj != 0) flags[f + r.y + dj] = tag;
+    }
+}
+
 // ---- event pass: clear old pixel, re-project, splat --------------------------------------------
 // One thread per event, CTA `rank` of the group owns a contiguous chunk (same chunk every
 // iteration, so each thread re-reads the state it wrote itself).
@@ -248,47 +292,48 @@ struct EventCtx {
     u64 *img_new;
     unsigned *flags;
     unsigned tag;
+    const int2 *row_tab;
+    const short2 *col_tab;
 };
 
+// `st` carries the event's state in and, when the event is (re-)projected, its new state out.
 template <int SH>
-__device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 st, float2 *st_slot, double2 *pr_slot,
-                                          double2 *nxy_slot) {
+__device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 &st, double2 *pr_slot, double2 *nxy_slot) {
     const unsigned frx_u = e.x & 0xffffu;
     const unsigned fry_raw = e.x >> 16;
     const bool noise = (fry_raw & BF_EVENT_NOISE) != 0;
     const unsigned fry_u = fry_raw & 0x7fffu;
     const int t = (int)e.y;
-    const float frx = (float)frx_u, fry = (float)fry_u, tf = (float)t;
+    // float(fr) of event.h:165-167 is exact for 16-bit coordinates, so its f64 value is fr itself
+    const double frx = u32_to_double(frx_u), fry = u32_to_double(fry_u);
+    const float tf = (float)t;
     double prx, pry;
-    if (c.first) { prx = (double)frx_u; pry = (double)fry_u; }                     // Event::reset (event.h:54-59)
+    if (c.first) { prx = frx; pry = fry; }                                         // Event::reset (event.h:54-59)
     else { prx = warp_from_m(st.x, frx); pry = warp_from_m(st.y, fry); }           // = the pr computed last time
     int x, y;
     double ex = 0.0, ey = 0.0;
     float mx = 0.0f, my = 0.0f;
     if (c.project) project_event(prx, pry, ex, ey, mx, my, frx, fry, tf, c.q);
-    if (st_slot != nullptr && (c.project || c.first)) *st_slot = make_float2(mx, my);
+    if (c.project || c.first) st = make_float2(mx, my);
     if (pr_slot != nullptr) *pr_slot = make_double2(prx, pry);
     if (nxy_slot != nullptr) *nxy_slot = make_double2(ex, ey);
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
         atomicAdd(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
-        mark_cells<SH>(c.flags, c.tag, x, y, c.n_ci, c.n_cj);
+        mark_cells_tab(c.flags, c.tag, x, y, c.row_tab, c.col_tab);
     }
 }
 
 template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, bool first, bool project, u64 *img_new,
-                           double2 *out_nxy, unsigned *flags, unsigned tag) {
+                           double2 *out_nxy, unsigned *flags, unsigned tag, const int2 *row_tab, const short2 *col_tab) {
     typedef CellCfg<SH> C;
     const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
     const int lo = rank * per;
     const int cnt = min(sd.n, lo + per) - lo;
     if (cnt <= 0) return;
-    const bf_event *ev = P.events + sd.ev_off + lo;
-    float2 *state = P.state + sd.ev_off + lo;
-    double2 *nxy = out_nxy ? out_nxy + sd.ev_off + lo : nullptr;
-    double2 *pro = out_nxy ? P.pr_out + sd.ev_off + lo : nullptr;   // per-event outputs come as a pair
+    const bool pro = out_nxy != nullptr;   // per-event outputs (pr, nx/ny) come as a pair
     EventCtx c;
     make_pixel_map(c.pm, g, P.pitch);
     c.q = q;
@@ -296,38 +341,78 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
     c.n_cj = (g.cols + C::CW - 1) / C::CW;
     c.first = first; c.project = project; c.img_new = img_new; c.flags = flags; c.tag = tag;
-    // software pipeline: the loads of trip n+1 are issued before trip n is processed
-    int i = (int)threadIdx.x;
-    uint2 e0 = make_uint2(0u, 0u), e1 = e0;
-    float2 s0 = make_float2(0.0f, 0.0f), s1 = s0;
-    if (i < cnt) {
-        e0 = ld_nc_u32x2(ev + i);
-        if (!first) s0 = state[i];
-        if (i + BF_NT < cnt) {
-            e1 = ld_nc_u32x2(ev + i + BF_NT);
-            if (!first) s1 = state[i + BF_NT];
-        }
+    c.row_tab = row_tab; c.col_tab = col_tab;
+    // Events are taken in PAIRS aligned in the batch arrays (one 16-byte load brings two events, one
+    // more their two states, one 16-byte store writes the states back); a pair that straddles the
+    // chunk boundary has its foreign half predicated off.  Software pipeline: the loads of trip
+    // n+1 are issued before trip n is processed.
+    const long long gs = sd.ev_off + lo, ge = gs + cnt;          // this CTA's events, batch-global indices
+    const long long p0 = gs >> 1, p1 = (ge + 1) >> 1;            // pairs [p0, p1)
+    const uint4 *ev4 = reinterpret_cast<const uint4 *>(P.events);
+    float4 *st4 = reinterpret_cast<float4 *>(P.state);
+    long long p = p0 + (long long)threadIdx.x;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    float4 st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (p < p1) {
+        e = ld_nc_u32x4(ev4 + p);
+        if (!first) st = st4[p];
     }
-    for (; i < cnt; i += 2 * BF_NT) {
-        const int k = i + BF_NT;
-        const bool two = k < cnt;
-        const int ni = i + 2 * BF_NT, nk = ni + BF_NT;
-        uint2 n0 = make_uint2(0u, 0u), n1 = n0;
-        float2 t0 = make_float2(0.0f, 0.0f), t1 = t0;
-        if (ni < cnt) {
-            n0 = ld_nc_u32x2(ev + ni);
-            if (!first) t0 = state[ni];
-            if (nk < cnt) {
-                n1 = ld_nc_u32x2(ev + nk);
-                if (!first) t1 = state[nk];
-            }
+    for (; p < p1; p += BF_NT) {
+        const long long np = p + BF_NT;
+        uint4 ne = make_uint4(0u, 0u, 0u, 0u);
+        float4 nst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (np < p1) {
+            ne = ld_nc_u32x4(ev4 + np);
+            if (!first) nst = st4[np];
         }
+        const long long i0 = 2 * p, i1 = i0 + 1;
+        const bool v0 = i0 >= gs, v1 = i1 < ge;                  // (i0 < ge and i1 >= gs hold by construction)
+        float2 w0 = make_float2(st.x, st.y), w1 = make_float2(st.z, st.w);
+        if (v0) event_one<SH>(c, make_uint2(e.x, e.y), w0, pro ? P.pr_out + i0 : nullptr, out_nxy ? out_nxy + i0 : nullptr);
+        if (v1) event_one<SH>(c, make_uint2(e.z, e.w), w1, pro ? P.pr_out + i1 : nullptr, out_nxy ? out_nxy + i1 : nullptr);
         // the final pass (no splat) only reads the state; every other pass rewrites it
-        float2 *w0 = img_new ? state + i : nullptr, *w1 = img_new ? state + k : nullptr;
-        event_one<SH>(c, e0, s0, w0, pro ? pro + i : nullptr, nxy ? nxy + i : nullptr);
-        if (two) event_one<SH>(c, e1, s1, w1, pro ? pro + k : nullptr, nxy ? nxy + k : nullptr);
-        e0 = n0; e1 = n1; s0 = t0; s1 = t1;
+        if (img_new != nullptr) {
+            if (v0 && v1) st4[p] = make_float4(w0.x, w0.y, w1.x, w1.y);
+            else if (v0) P.state[i0] = w0;
+            else if (v1) P.state[i1] = w1;
+        }
+        e = ne; st = nst;
     }
+}
+
+// ---- fast unpack of a packed box sum ---------------------------------------------------------------
+// bf_unpack_avg (bf_logic.h) is the specification: s = f32(sum_t / 1e9), mean = s / f32(cnt).  It is
+// ~20 % of all instructions of the minimise kernel when written naively (64-bit shifts, an s64 -> f64
+// conversion, an IEEE f32 divide with its MUFU.RCP + Newton step).  When BfPack::fast holds
+// (q == 0, no offset, sums < 2^52) the same bits are obtained with:
+//   * cnt from the high word only (cnt_shift >= 32 always);
+//   * sum -> f64 by the 2^52 exponent trick (one LOP3 + one DADD, exact for sums < 2^52);
+//   * the divide as Markstein's correction  q0 = s*y, q = fma(fma(-c, q0, s), y, q0)  with
+//     y = RN(1/c) read from a per-CTA table: correctly rounded for every f32 s and integer
+//     c < BF_RCP_TAB, because  (i) |q0 - s/c| <= 1.5 ulp, so the computed q0 + rem*y differs from
+//     the exact quotient by < 2^-23 ulp, and (ii) s/c with c < 2^17 is never closer than 2^-18 ulp
+//     to a rounding boundary without lying on it, which it cannot (c*(25-bit odd) has no 24-bit
+//     representation).  tests/test_divconst.py checks the sequence against IEEE division.
+#define BF_RCP_TAB 1024
+__device__ __forceinline__ void fill_rcp_table(float2 *tab) {
+    for (int c = threadIdx.x; c < BF_RCP_TAB; c += blockDim.x) {
+        const float cf = (float)c;
+        tab[c] = make_float2(cf, c ? __fdiv_rn(1.0f, cf) : 0.0f);
+    }
+}
+__device__ __forceinline__ float unpack_avg_fast(const BfPack &pk, const float2 *tab, u64 v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned cnt = hi >> (pk.cnt_shift - 32);
+    const unsigned mhi = (unsigned)(pk.sum_mask >> 32);
+    const double a = __dsub_rn(__hiloint2double((int)((hi & mhi) | 0x43300000u), (int)lo), 4503599627370496.0);
+    const double q0 = __dmul_rn(a, 1e-9);
+    const float s = (float)__fma_rn(__fma_rn(-1000000000.0, q0, a), 1e-9, q0);
+    if (cnt < BF_RCP_TAB) {
+        const float2 cy = tab[cnt];
+        const float f0 = __fmul_rn(s, cy.y);
+        return __fmaf_rn(__fmaf_rn(-cy.x, f0, s), cy.y, f0);
+    }
+    return __fdiv_rn(s, (float)cnt);
 }
 
 // ---- image pass ------------------------------------------------------------------------------------
@@ -352,9 +437,9 @@ __device__ __forceinline__ void acc_zero(Acc &a) {
 //   unpack -> mean time f32                 A[r], r = 0..AR-1   (row ci*8 - 1 + r of the image)
 //   Scharr (accel_lib.h:594-605) + sums     lanes H..31-H, rows 1..8
 // Integer packed sums commute, so this equals the reference's per-event s x s splat exactly.
-template <int SH, bool MATERIALISE>
-__device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, int ci,
-                                             int cj, int rows, int cols, int i0, int j0, float *out_img,
+template <int SH, bool MATERIALISE, bool FAST>
+__device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, const float2 *rcp_tab,
+                                             int ci, int cj, int rows, int cols, int i0, int j0, float *out_img,
                                              float *out_gx, float *out_gy) {
     typedef CellCfg<SH> C;
     const int lane = threadIdx.x & 31;
@@ -377,7 +462,7 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
             a += __shfl_up_sync(0xffffffffu, v, d);
             a += __shfl_down_sync(0xffffffffu, v, d);
         }
-        A[r] = (a != 0ull) ? bf_unpack_avg(pk, a) : 0.0f;
+        A[r] = (a != 0ull) ? (FAST ? unpack_avg_fast(pk, rcp_tab, a) : bf_unpack_avg(pk, a)) : 0.0f;
     }
     // lanes whose +-SH neighbours fall outside the warp hold garbage in A; they are never outputs
     // (outputs are lanes H..31-H) nor neighbours of outputs (lanes H-1..32-H need lanes 0..31 only).
@@ -530,7 +615,7 @@ __device__ __forceinline__ void cell_clear(u64 *img, int pitch, int ci, int cj) 
 // Returns the number of live cells when the grid fits one list (else -1).
 template <int SH, bool MATERIALISE>
 __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
-                          const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
+                          const float2 *rcp_tab, const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
                           const unsigned *flags_clear, unsigned tag_clear, const unsigned short *list_prev,
                           int n_prev) {
@@ -545,10 +630,18 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
         if (img != nullptr) {
             const int total = compact_cells(flags, tag, base, n_cells, list, scan);
             if (one_chunk) n_live = total;
-            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
-                const int c = base + (int)list[k];
-                const int ci = c / n_cj, cj = c - ci * n_cj;
-                cell_process<SH, MATERIALISE>(acc, img, pitch, pk, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+            if (pk.fast) {
+                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                    const int c = base + (int)list[k];
+                    const int ci = c / n_cj, cj = c - ci * n_cj;
+                    cell_process<SH, MATERIALISE, true>(acc, img, pitch, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+                }
+            } else {
+                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                    const int c = base + (int)list[k];
+                    const int ci = c / n_cj, cj = c - ci * n_cj;
+                    cell_process<SH, MATERIALISE, false>(acc, img, pitch, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+                }
             }
         }
         if (img_clear != nullptr && !(one_chunk && list_prev != nullptr)) {

@@ -55,7 +55,8 @@ BF_HD bool bf_guard_tiny(const BfGeom &g, int res_x, int res_y) {
 struct BfPack {
     int cnt_shift;           // 64 - cnt_bits
     int q;                   // time quantisation shift (0 = exact)
-    int32_t t_min;
+    int32_t t_min;           // offset subtracted from every t before packing (0 when all t >= 0 fit as they are)
+    int fast;                // 1: q == 0, t_min == 0 and every box sum < 2^52 (device fast unpack path)
     unsigned long long sum_mask;
 };
 
@@ -67,14 +68,25 @@ BF_HD int bf_bits(unsigned long long v) {
 
 BF_HD void bf_make_pack(BfPack &p, int n, int32_t t_min, int32_t t_max) {
     const int cnt_bits = bf_bits((unsigned long long)(n > 0 ? n : 1));
+    p.cnt_shift = 64 - cnt_bits;
+    p.sum_mask = (1ull << p.cnt_shift) - 1ull;
+    // Local times are normally >= 0 (t = timestamp - slice start): then they are packed as they are
+    // and the unpack needs no offset correction.  Only when that would not fit (or t < 0 occurs:
+    // events older than the slice start of an overflowed buffer, dvs_flow.h:187-190) the times are
+    // re-based to t_min.
+    if (t_min >= 0 && bf_bits((unsigned long long)t_max) + 2 * cnt_bits <= 64) {
+        p.q = 0;
+        p.t_min = 0;
+        p.fast = (bf_bits((unsigned long long)t_max) + cnt_bits <= 52) ? 1 : 0;
+        return;
+    }
     const unsigned long long span = (unsigned long long)((long long)t_max - (long long)t_min);
     const int t_bits = bf_bits(span);
     int q = t_bits + 2 * cnt_bits - 64;
     if (q < 0) q = 0;
     p.q = q;
     p.t_min = t_min;
-    p.cnt_shift = 64 - cnt_bits;
-    p.sum_mask = (1ull << p.cnt_shift) - 1ull;
+    p.fast = 0;
 }
 
 BF_HD unsigned long long bf_pack_value(const BfPack &p, int32_t t) {

@@ -24,6 +24,12 @@ void lg_pack(int n, int t_min, int t_max, int *cnt_shift, int *q) {
     *q = p.q;
 }
 
+void lg_pack_full(int n, int t_min, int t_max, int *out4) {
+    BfPack p;
+    bf_make_pack(p, n, t_min, t_max);
+    out4[0] = p.cnt_shift; out4[1] = p.q; out4[2] = p.t_min; out4[3] = p.fast;
+}
+
 // Accumulate n packed values (as the device's 64-bit atomic add would) and unpack the mean.
 float lg_accumulate(int n_total, int t_min, int t_max, int k, const int *t) {
     BfPack p;

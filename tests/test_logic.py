@@ -76,6 +76,27 @@ def test_packed_accumulator_quantises_only_beyond_64_bits(lg):
     assert q.value == 13
 
 
+def test_pack_offset_and_fast_path_selection(lg):
+    """Non-negative local times are packed without an offset (and take the device's fast unpack when
+    every possible box sum stays below 2^52); negative times or over-long spans re-base to t_min."""
+    def pack(n, lo, hi):
+        o = (C.c_int * 4)()
+        lg.lg_pack_full(n, lo, hi, o)
+        return tuple(o)
+    for n, span in [(30000, 10_000_000), (90000, 30_000_000), (100000, 50_000_000), (200000, 20_000_000),
+                    (1000000, 10_000_000), (50000, 200_000_000)]:
+        cs, q, off, fast = pack(n, 1234, span)
+        assert (q, off, fast) == (0, 0, 1)
+        assert n * span < (1 << 52)
+    assert pack(90000, -5, 30_000_000)[2:] == (-5, 0)                 # negative time: offset, generic path
+    cs, q, off, fast = pack(1 << 16, 1_000_000_000, 2_000_000_000)    # 31 + 2*17 > 64 as is, fits after re-basing
+    assert (q, off, fast) == (0, 1_000_000_000, 0)
+    cs, q, off, fast = pack(1 << 14, 0, (1 << 31) - 1)                # 31 + 15 = 46 bits: fast
+    assert (q, off, fast) == (0, 0, 1)
+    cs, q, off, fast = pack((1 << 21) - 1, 0, (1 << 22) - 1)          # fits in 64 but sums may reach 2^43 < 2^52: fast
+    assert (q, off, fast) == (0, 0, 1)
+
+
 def test_unpack_equals_exact_mean(lg):
     rng = np.random.default_rng(1)
     for _ in range(200):
@@ -85,6 +106,11 @@ def test_unpack_equals_exact_mean(lg):
         s = np.float32(np.float64(int(t.astype(np.int64).sum())) / 1e9)
         want = np.float32(s / np.float32(k))
         assert np.float32(got) == want
+        # the same events with non-negative times (no offset in the packed word)
+        t2 = (t.astype(np.int64) + 2_000_000).astype(np.int32)
+        got2 = lg.lg_accumulate(90000, 0, 32_000_000, k, t2.ctypes.data_as(C.POINTER(C.c_int)))
+        s2 = np.float32(np.float64(int(t2.astype(np.int64).sum())) / 1e9)
+        assert np.float32(got2) == np.float32(s2 / np.float32(k))
 
 
 def test_gd_control_flow_replay_matches_oracle(lg, oracle_port):

@@ -5,8 +5,9 @@ sass_csv, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 # collect (file,line) per instruction of the kernel, in order
 lines = []
 in_k = False; cur = ("?", 0)
