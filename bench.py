@@ -212,7 +212,7 @@ def main():
         stage[off:off + n] = bf.pack_events(s.fr_x, s.fr_y, s.t_ns)
         ctx.add_staged(off, n, SCALE, MAX_ITER)
         off += n
-    h2d = n_events * 8 + len(slices) * 112
+    h2d = n_events * 8 + len(slices) * 120   # 8-byte event records + the slice table
     d2h = len(slices) * bf.RESULT_BYTES
 
     gather_buf = None

@@ -60,6 +60,7 @@ ABI_SYMBOLS = (
     "bf_batch_result", "bf_batch_events", "bf_minimize", "bf_time_img", "bf_fast_model", "bf_project",
     "bf_ctx_set_stream", "bf_batch_results_device", "bf_debug_profile", "bf_model_from_image",
     "bf_batch_run_streamed",
+    "bf_batch_add_local", "bf_batch_slot_mode", "bf_local_minimize",
     "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
@@ -117,6 +118,9 @@ def load() -> C.CDLL:
         lib.bf_project.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_double, C.c_double]
+        lib.bf_batch_add_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.bf_batch_slot_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.bf_local_minimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceResult)]
         lib.bf_multi_create.restype = C.c_void_p
         lib.bf_multi_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]
         for name in ("bf_multi_destroy", "bf_multi_device_count", "bf_multi_reset", "bf_multi_sync", "bf_multi_size"):
@@ -241,6 +245,30 @@ class Context:
         m = Model.from_array(init) if init is not None else None
         return self._chk(self.lib.bf_batch_add_staged(self.h, int(offset), int(n), scale, max_iter,
                                                       C.byref(m) if m is not None else None))
+
+    def add_local(self, fr_x, fr_y, t_ns, scale=3):
+        """Queue a cloud for OptimizerLocal::run (contrast-driven nx, ny descent)."""
+        fx = np.ascontiguousarray(fr_x, dtype=np.uint16)
+        fy = np.ascontiguousarray(fr_y, dtype=np.uint16)
+        t = np.ascontiguousarray(t_ns, dtype=np.int32)
+        return self._chk(self.lib.bf_batch_add_local(self.h, _ptr(fx), _ptr(fy), _ptr(t), len(fx), scale))
+
+    def slot_mode(self, slot, mode):
+        self._chk(self.lib.bf_batch_slot_mode(self.h, slot, mode))
+
+    @staticmethod
+    def local_view(res: dict) -> dict:
+        """Names for the fields of an OptimizerLocal result record (see include/bf_cuda.h)."""
+        m = res["model"]
+        return {"rc": res["rc"], "steps": res["iters"], "nx": m[7], "ny": m[8], "score": m[2], "dnx": m[3], "dny": m[4],
+                "dn_th": m[5], "nz_cnt": int(m[6]), "img_rows": res["img_rows"], "img_cols": res["img_cols"],
+                "n_events": res["n_events"]}
+
+    def local_minimize(self, fr_x, fr_y, t_ns, scale=3):
+        self.reset()
+        self.add_local(fr_x, fr_y, t_ns, scale)
+        self.run()
+        return self.local_view(self.result(0))
 
     def upload(self):
         self._chk(self.lib.bf_batch_upload(self.h))

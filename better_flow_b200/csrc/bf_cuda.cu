@@ -31,6 +31,7 @@ struct __align__(16) Smem {
     BfPack pk;
     BfProj proj;
     BfOpt opt;
+    LocalOpt lopt;
     int cont;
     int guard;
     int minmax[6];
@@ -133,6 +134,66 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
 #undef PF_MARK
 }
 
+// OptimizerLocal::run (optimizer_sampler.cpp:4-38) for the slice in S.sd: same double-buffered
+// event pass -> barrier -> image pass -> barrier -> control step cycle as run_slice, one cycle per
+// iteration_step.
+template <int SH>
+__device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
+                                int rank) {
+    u64 *img0 = P.images + (size_t)group * 2 * P.img_elems;
+    u64 *img1 = img0 + P.img_elems;
+    unsigned *flags0 = P.flags + (size_t)group * 2 * P.flag_elems;
+    unsigned *flags1 = flags0 + P.flag_elems;
+    double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
+    int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
+    short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
+    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
+    if (threadIdx.x == 0) local_opt_init(S.lopt, S.g.scale);
+    __syncthreads();
+    int buf = 0;
+    int n_prev = -1;
+    for (int iter = 0;; ++iter) {
+        u64 *img_new = buf ? img1 : img0;
+        u64 *img_old = buf ? img0 : img1;
+        unsigned *flags_new = buf ? flags1 : flags0;
+        unsigned *flags_old = buf ? flags0 : flags1;
+        tag += 1;
+        local_event_pass<SH>(P, S.sd, S.g, S.pk, S.lopt.cur_nx, S.lopt.cur_ny, rank, img_new, flags_new, tag, row_tab, col_tab);
+        group_barrier(&ws->bar, bar_target, P.G);
+        Acc acc;
+        acc_zero(acc);
+        n_prev = image_pass<SH, false, 1>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, P.G, S.list[buf],
+                                          S.scan, nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
+                                          n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
+        acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
+        group_barrier(&ws->bar, bar_target, P.G);
+        if (threadIdx.x < 32) {
+            BfSums s;
+            group_sums(s, partials, P.G);
+            if (threadIdx.x == 0) S.cont = local_opt_advance(S.lopt, s.cnt, s.si, P.iter_cap) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!S.cont) break;
+        buf ^= 1;
+    }
+    {
+        Acc none;
+        image_pass<SH, false, 1>(none, nullptr, P.pitch, S.g, S.pk, S.rcp_tab, nullptr, 0u, rank, P.G, S.list[buf ^ 1], S.scan,
+                                 nullptr, nullptr, nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag,
+                                 n_prev >= 0 ? S.list[buf] : nullptr, n_prev);
+    }
+    // results in the slots of bf_slice_result documented in include/bf_cuda.h (bf_batch_add_local)
+    if (threadIdx.x == 0) {
+        bf_opt_init(S.opt, nullptr);
+        S.opt.m.total_dx = S.lopt.nx; S.opt.m.total_dy = S.lopt.ny;
+        S.opt.m.dx = S.lopt.last_score; S.opt.m.dy = S.lopt.dnx; S.opt.m.rot = S.lopt.dny; S.opt.m.div = S.lopt.dn_th;
+        S.opt.m.cnt = S.lopt.nz_cnt;
+        S.opt.iters = S.lopt.steps; S.opt.rc = S.lopt.rc;
+        S.opt.x_div = S.opt.y_div = S.opt.rot_div = S.opt.div_div = 0.0f;
+    }
+    __syncthreads();
+}
+
 // MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
 // (twice the warps to hide L2 latency, at the price of a few spills).
 template <int MINB>
@@ -221,14 +282,18 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             bf_make_geom(S.g, x_min, x_max, y_min, y_max, S.sd.scale);
             bf_make_pack(S.pk, S.sd.n, t_min, t_max);
             S.guard = 0;
-            if (bf_guard_tiny(S.g, P.res_x, P.res_y)) S.guard = 1;         // :49-55
-            else if (S.sd.n < P.min_events) S.guard = 2;                   // :57-58
+            if (bf_guard_tiny(S.g, P.res_x, P.res_y)) S.guard = 1;         // :49-55 (and optimizer_sampler.cpp:9-13)
+            else if (S.sd.mode == 0 && S.sd.n < P.min_events) S.guard = 2; // :57-58 (OptimizerLocal has no such guard)
+            else if (S.sd.n == 0) S.guard = 2;
         }
         __syncthreads();
         const int guard = S.guard;
         if (pf && threadIdx.x == 0) pf[PF_PROLOGUE] += clock64() - t_pro;
 
-        if (guard == 0) {
+        if (guard == 0 && S.sd.mode == 1) {
+            if (S.sd.scale == 1) run_slice_local<0>(P, S, ws, bar_target, tag, group, rank);
+            else run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
+        } else if (guard == 0) {
             switch (S.sd.scale) {
                 case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank); break;
                 case 3: run_slice<1>(P, S, ws, bar_target, tag, group, rank); break;
@@ -238,7 +303,9 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
             S.opt.rc = BF_RC_SKIPPED;
         }
-        if (guard != 0 && S.sd.has_init && P.want_events) {
+        if (S.sd.mode == 1) {
+            // OptimizerLocal keeps no per-event state on the device (pr is a closed form of nx, ny)
+        } else if (guard != 0 && S.sd.has_init && P.want_events) {
             // set_model already re-projected the events before run() bailed out (dvs_flow.h:218-222)
             if (threadIdx.x == 0) {
                 const bf_model &m = S.sd.init;
@@ -264,7 +331,7 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             r.img_rows = S.g.rows; r.img_cols = S.g.cols;
             r.x_shift = S.g.x_shift; r.y_shift = S.g.y_shift;
             r.n_events = S.sd.n;
-            r.flags = (guard == 1 ? BF_FLAG_ALL_NOISE : 0u) | (S.pk.q > 0 ? BF_FLAG_T_QUANTISED : 0u);
+            r.flags = ((guard == 1 && S.sd.mode == 0) ? BF_FLAG_ALL_NOISE : 0u) | (S.pk.q > 0 ? BF_FLAG_T_QUANTISED : 0u);
             P.results[slice] = r;
         }
         parity ^= 1;
@@ -783,6 +850,35 @@ int bf_batch_add(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const in
     const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
     if (slot >= 0) c->n_events += n;
     return slot;
+}
+
+// OptimizerLocal(LinearEventCloud*, scale) (optimizer_sampler.h:41-56): the slice is minimised by
+// OptimizerLocal::run instead of OptimizerRolling::run.
+int bf_batch_add_local(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, int n, int scale) {
+    if (scale != 1 && scale != 3) return fail(BF_ERR_ARG, "bf_batch_add_local: scale %d unsupported (1 or 3)", scale);
+    const int slot = bf_batch_add(c, fr_x, fr_y, t_ns, nullptr, n, scale, -1, nullptr);
+    if (slot >= 0) c->h_slices[slot].mode = 1;
+    return slot;
+}
+
+int bf_batch_slot_mode(bf_ctx *c, int slot, int mode) {
+    if (!c || slot < 0 || slot >= c->n_slices || (mode != 0 && mode != 1)) return fail(BF_ERR_ARG, "bf_batch_slot_mode: bad arguments");
+    if (mode == 1 && c->h_slices[slot].scale > 3) return fail(BF_ERR_ARG, "OptimizerLocal mode supports scale 1 or 3");
+    c->h_slices[slot].mode = mode;
+    c->uploaded = c->ran = false;
+    return BF_OK;
+}
+
+int bf_local_minimize(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, int n, int scale,
+                      bf_slice_result *out) {
+    int rc;
+    if ((rc = bf_batch_reset(c)) != BF_OK) return rc;
+    if ((rc = bf_batch_add_local(c, fr_x, fr_y, t_ns, n, scale)) < 0) return rc;
+    if ((rc = bf_batch_run(c, 0)) != BF_OK) return rc;
+    bf_slice_result r;
+    if ((rc = bf_batch_result(c, 0, &r)) != BF_OK) return rc;
+    if (out) *out = r;
+    return r.rc;
 }
 
 int bf_batch_add_packed(bf_ctx *c, const bf_event *events, int n, int scale, int max_iter, const bf_model *init) {

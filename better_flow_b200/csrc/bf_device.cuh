@@ -58,6 +58,8 @@ struct SliceDesc {
     int scale;
     int max_iter;
     int has_init;
+    int mode;           // 0: OptimizerRolling::run, 1: OptimizerLocal::run
+    int pad_;
     bf_model init;
 };
 
@@ -613,7 +615,12 @@ __device__ __forceinline__ void cell_clear(u64 *img, int pitch, int ci, int cj) 
 // every sensor up to ~VGA) the previous iteration's compacted list is simply kept in shared memory
 // (`list_prev`, `n_prev`) and no second scan is needed; larger grids re-scan the other flag array.
 // Returns the number of live cells when the grid fits one list (else -1).
-template <int SH, bool MATERIALISE>
+template <int SH> __device__ __forceinline__ void local_cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk,
+                                                                    int ci, int cj, int rows, int cols);
+
+// MODE 0: mean-timestamp image + Scharr + moments (OptimizerRolling); MODE 1: saturated event-count
+// image + Gaussian blur + non-zero mean (OptimizerLocal, see local_cell_process).
+template <int SH, bool MATERIALISE, int MODE = 0>
 __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
                           const float2 *rcp_tab, const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
@@ -630,7 +637,13 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
         if (img != nullptr) {
             const int total = compact_cells(flags, tag, base, n_cells, list, scan);
             if (one_chunk) n_live = total;
-            if (pk.fast) {
+            if constexpr (MODE == 1) {
+                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                    const int c = base + (int)list[k];
+                    const int ci = c / n_cj, cj = c - ci * n_cj;
+                    local_cell_process<SH>(acc, img, pitch, pk, ci, cj, g.rows, g.cols);
+                }
+            } else if (pk.fast) {
                 for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
                     const int c = base + (int)list[k];
                     const int ci = c / n_cj, cj = c - ci * n_cj;
@@ -659,6 +672,154 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
         }
     }
     return n_live;
+}
+
+// ====================================================================================================
+// OptimizerLocal on the device (reference: src/optimizer_sampler.cpp): the
+// contrast-driven coordinate descent over a global (nx, ny).  Same machinery as the rolling path --
+// point splat with one 64-bit atomic, generation-tagged live cells, one warp per cell in registers --
+// with a different per-cell function and a different (much simpler) per-event warp.
+// ====================================================================================================
+
+// OptimizerLocal::iteration_step's image (optimizer_sampler.cpp:124-149) for one cell:
+//   count image  C = min(255, s x s box sum of the point counts)   (the reference increments a u8 with
+//                    saturation per splatted pixel, :139-145: the result is min(255, #increments));
+//   blur         B = cv::GaussianBlur(C, Size(s, s), 0, 0) on CV_8UC1 = binomial [1 2 1]/4 per axis in fixed
+//                    point, i.e. (sum + 8) >> 4 for s = 3, BORDER_REFLECT_101 at the image edges; s = 1: B = C;
+//   score sums   number and sum of the non-zero B (get_event_score, :192-204) -> acc.cnt, acc.si.
+template <int SH>
+__device__ __forceinline__ void local_cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, int ci, int cj,
+                                                   int rows, int cols) {
+    typedef CellCfg<SH> C;
+    static_assert(SH <= 1, "OptimizerLocal on the device supports scale 1 and 3 (scale 5 needs a 4-pixel halo)");
+    const int lane = threadIdx.x & 31;
+    const u64 *p = img + (long long)(ci * BF_CELL_ROWS - C::H + BF_BORDER) * pitch + (cj * C::CW - C::H + BF_BORDER + lane);
+    u64 P[C::PR];
+#pragma unroll
+    for (int r = 0; r < C::PR; ++r) P[r] = __ldcg(p + (long long)r * pitch);
+    int Cn[C::AR];   // count image rows ci*8 - 1 .. ci*8 + 8
+#pragma unroll
+    for (int r = 0; r < C::AR; ++r) {
+        u64 v = 0;
+#pragma unroll
+        for (int d = 0; d <= 2 * SH; ++d) v += P[r + d];
+        u64 a = v;
+#pragma unroll
+        for (int d = 1; d <= SH; ++d) {
+            a += __shfl_up_sync(0xffffffffu, v, d);
+            a += __shfl_down_sync(0xffffffffu, v, d);
+        }
+        const unsigned cnt = (unsigned)(a >> 32) >> (pk.cnt_shift - 32);
+        Cn[r] = (int)min(cnt, 255u);
+    }
+    const int j = cj * C::CW + lane - C::H;
+    const bool out_lane = (lane >= C::H) && (lane < 32 - C::H) && j < cols;
+    int n_nz = 0, s_nz = 0;
+    if (SH == 0) {
+#pragma unroll
+        for (int r = 1; r <= BF_CELL_ROWS; ++r) {
+            const int i = ci * BF_CELL_ROWS + r - 1;
+            if (out_lane && i < rows && Cn[r] > 0) { n_nz += 1; s_nz += Cn[r]; }
+        }
+    } else {
+        // BORDER_REFLECT_101 rows: image row -1 := row 1, image row `rows` := row rows - 2
+        if (ci == 0) Cn[0] = Cn[2];
+#pragma unroll
+        for (int r = 2; r < C::AR; ++r)
+            if (ci * BF_CELL_ROWS - 1 + r == rows) Cn[r] = Cn[r - 2];
+#pragma unroll
+        for (int r = 1; r <= BF_CELL_ROWS; ++r) {
+            const int i = ci * BF_CELL_ROWS + r - 1;
+            const int V = Cn[r - 1] + 2 * Cn[r] + Cn[r + 1];
+            int L = __shfl_up_sync(0xffffffffu, V, 1), R = __shfl_down_sync(0xffffffffu, V, 1);
+            if (j == 0) L = R;               // column -1 := column 1
+            if (j == cols - 1) R = L;        // column `cols` := column cols - 2
+            const int B = (L + 2 * V + R + 8) >> 4;
+            if (out_lane && i < rows && B > 0) { n_nz += 1; s_nz += B; }
+        }
+    }
+    acc.cnt += n_nz;
+    acc.si += s_nz;
+}
+
+// State of OptimizerLocal::run (optimizer_sampler.cpp:4-38, 90-117).
+struct LocalOpt {
+    double nx, ny;            // accepted position
+    double dnx, dny, dn_th;
+    double last_score;
+    double cur_nx, cur_ny;    // position of the iteration_step being evaluated
+    int phase;                // 0: initial step, 1: compute_new_nx's step, 2: compute_new_ny's step
+    int steps, rc;
+    unsigned nz_cnt;          // non-zero pixels of the last image
+};
+
+__device__ __forceinline__ void local_opt_init(LocalOpt &o, int scale) {
+    o.nx = 0; o.ny = 0; o.last_score = 0;                                          // :5-6
+    o.dnx = 0.01; o.dny = 0.01;                                                    // :7
+    o.dn_th = (127 * 1 * 1000.0) / (double)(10ull * (unsigned long long)scale * 100000000ull);   // NZ*T_DIVIDER*1000 / (10*scale*FROM_MS(MAX_TIME_MS))
+    o.cur_nx = 0; o.cur_ny = 0; o.phase = 0; o.steps = 0; o.rc = BF_RC_OK; o.nz_cnt = 0;
+}
+
+// Consumes the score of the step at (cur_nx, cur_ny) and sets up the next one; false when run() is over.
+__device__ __forceinline__ bool local_opt_advance(LocalOpt &o, double cnt, double sum, int iter_cap) {
+    const double score = cnt > 0 ? sum / cnt : 0.0;                                // :192-204
+    o.nz_cnt = (unsigned)cnt;
+    o.steps += 1;
+    if (o.phase == 0) {
+        o.last_score = score;                                                      // :16
+    } else {
+        const double dscore = score - o.last_score;                                // :94-95 / :109-110
+        o.last_score = score;
+        if (o.phase == 1) { if (dscore <= 0) o.dnx = -o.dnx / 2.0; o.nx = o.cur_nx; }   // :97-101, run() assigns nx
+        else { if (dscore <= 0) o.dny = -o.dny / 2.0; o.ny = o.cur_ny; }
+    }
+    if (o.phase != 1) {
+        if (!(hypot(o.dnx, o.dny) > o.dn_th)) return false;                        // while condition, :20
+        if (o.steps >= iter_cap) { o.rc = BF_RC_ITER_CAP; return false; }
+        o.phase = 1; o.cur_nx = o.nx + o.dnx; o.cur_ny = o.ny;                     // compute_new_nx
+    } else {
+        o.phase = 2; o.cur_nx = o.nx; o.cur_ny = o.ny + o.dny;                     // compute_new_ny
+    }
+    return true;
+}
+
+// Event pass of one iteration_step (optimizer_sampler.cpp:121, 126-145): Event::project(nx, ny)
+// (event.h:65-70 -> 164-168), pixel with the UNtruncated double shifts, window test on the truncated
+// ints before the + scale/2 (:133-137), point splat.  No per-event state: the warp is absolute.
+template <int SH>
+__device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk, double nx,
+                                 double ny, int rank, u64 *img_new, unsigned *flags, unsigned tag, const int2 *row_tab,
+                                 const short2 *col_tab) {
+    const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
+    const int lo = rank * per;
+    const int cnt = min(sd.n, lo + per) - lo;
+    if (cnt <= 0) return;
+    const float kx = (float)((double)(float)nx / 127.0), ky = (float)((double)(float)ny / 127.0);   // event.h:164-165
+    // event_c = Event((x_max - x_min) / 2 + x_min, ..., t = 0): project() leaves it at float(fr)  (optimizer_sampler.h:51, .cpp:122)
+    const double sc = (double)g.scale;
+    const double cx = (double)(float)(unsigned)((g.x_max - g.x_min) / 2 + g.x_min);
+    const double cy = (double)(float)(unsigned)((g.y_max - g.y_min) / 2 + g.y_min);
+    const double x_shift = __dadd_rn(__dmul_rn(-cx, sc), (double)g.w / 2.0);      // :126-127
+    const double y_shift = __dadd_rn(__dmul_rn(-cy, sc), (double)g.h / 2.0);
+    const u64 one = 1ull << pk.cnt_shift;
+    const long long gs = sd.ev_off + lo, ge = gs + cnt;
+    const bf_event *ev = P.events;
+    for (long long i = gs + (long long)threadIdx.x; i < ge; i += BF_NT) {
+        const uint2 e = ld_nc_u32x2(ev + i);
+        const unsigned frx_u = e.x & 0xffffu, fry_u = (e.x >> 16) & 0x7fffu;
+        const int t = (int)e.y;
+        const float tf = (float)t;
+        const double prx = warp_from_m(__fmul_rn(kx, tf), u32_to_double(frx_u));   // event.h:167-168
+        const double pry = warp_from_m(__fmul_rn(ky, tf), u32_to_double(fry_u));
+        const int x = __double2int_rz(__dadd_rn(__dmul_rn(prx, sc), x_shift));    // :130-131
+        const int y = __double2int_rz(__dadd_rn(__dmul_rn(pry, sc), y_shift));
+        if ((unsigned)x < (unsigned)g.w && (unsigned)y < (unsigned)g.h) {         // :133-134
+            const int xc = x + g.half, yc = y + g.half;                           // :136-137
+            const u64 dt = (u64)((long long)t - (long long)pk.t_min);
+            atomicAdd(img_new + pixel_offset(xc, yc, P.pitch), one + (dt >> pk.q));
+            mark_cells_tab(flags, tag, xc, yc, row_tab, col_tab);
+        }
+    }
 }
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):

@@ -9,6 +9,8 @@
 //     by ONE persistent-kernel launch (bf_batch_*),
 //   * set_gpus(n): the queued batch is dealt to n devices (bf_multi_*: one launch per device, one
 //     NCCL all-gather of the per-slice flow records),
+//   * set_optimizer_local(): minimise every slice with OptimizerLocal (contrast-driven nx, ny descent)
+//     instead of OptimizerRolling; the slice's model then carries total_dx = -nx, total_dy = -ny,
 //   * set_flow_out(stream): one machine-readable line per slice,
 //   * set_quiet(): suppress the reference's per-slice dump of every past model.
 // Video / picture generation and the interactive mode are GUI features and are accepted but ignored.
@@ -22,6 +24,7 @@
 #include <better_flow/event.h>
 #include <better_flow/event_file.h>
 #include <better_flow/optimizer_rolling.h>
+#include <better_flow/optimizer_sampler.h>
 
 template <size_t MAX_SZ, sll SPAN> class DVS_flow {
 public:
@@ -56,6 +59,7 @@ protected:
     std::vector<Pending> pending_;
     int batch_;
     int gpus_;
+    bool local_;
     bool quiet_;
     std::ostream *flow_out_;
     ull slices_done_;
@@ -66,14 +70,14 @@ public:
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time = 0)
         : on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
-          scale(3), stm_disable(false), batch_(1), gpus_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          scale(3), stm_disable(false), batch_(1), gpus_(1), local_(false), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
           iters_done_(0) {}
 
     // run-time sized variant (CLI flags --max-events / --slice-time)
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time, size_t capacity, sll span)
         : ev_buffer(capacity, span), on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
-          scale(3), stm_disable(false), batch_(1), gpus_(1), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
+          scale(3), stm_disable(false), batch_(1), gpus_(1), local_(false), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
           iters_done_(0) {}
 
     ~DVS_flow() {}
@@ -105,6 +109,7 @@ public:
     // extensions
     void set_batch(int n) { batch_ = n < 1 ? 1 : n; }
     void set_gpus(int n) { gpus_ = n < 1 ? 1 : n; }
+    void set_optimizer_local(bool v = true) { local_ = v; }
     void set_quiet(bool q = true) { quiet_ = q; }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
     ObjectModel get_last_model() { return last_model; }
@@ -169,7 +174,35 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
     log.ts_first = log.size ? e_ptrs[0].timestamp : 0;
     log.ts_last = log.size ? e_ptrs[log.size - 1].timestamp : 0;
 
-    if (batch_ > 1 && stm_disable) {
+    if (local_) {
+        // OptimizerLocal works on a LinearEventCloud of its own and never warm-starts
+        LinearEventCloud cloud;
+        cloud.reserve(log.size);
+        for (auto &e : e_ptrs) {
+            e.reset();
+            e.set_local_time(start);
+            cloud.push_back(e);
+        }
+        OptimizerLocal optimizer(&cloud, scale);
+        const int rc = optimizer.run();
+        log.model = ObjectModel();
+        log.model.total_dx = -optimizer.get_nx();   // same sign convention as OptimizerRolling's totals:
+        log.model.total_dy = -optimizer.get_ny();   // events are projected with n = -total (optimizer_rolling.h:340-344)
+        log.model.dx = optimizer.get_score();
+        size_t k = 0;
+        for (auto &e : e_ptrs) {
+            Event &c = cloud[k++];
+            e.pr_x = c.pr_x; e.pr_y = c.pr_y; e.nx = c.nx; e.ny = c.ny;
+            e.compute_uv();
+            if (rc == 0) e.assume_score(0);
+        }
+        log_slice(log, optimizer.steps(), rc);
+        if (accumulate) {
+            LinearEventCloudTemplate<Event> cur;
+            for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);
+            accumulated.push_back(cur);
+        }
+    } else if (batch_ > 1 && stm_disable) {
         // independent slice: snapshot it and minimise later together with its neighbours
         Pending p;
         p.slice_start = start;

@@ -36,6 +36,7 @@ static int sensor_w = 240, sensor_h = 180;
 static char *flowOutName = NULL;
 static int batch = 1;
 static int gpus = 1;
+static bool optimizer_local = false;
 static int device = 0;
 
 static void lPrintVersion() {
@@ -73,6 +74,8 @@ static void usage(int ret) {
     printf("    [--batch=N]\t\t\t\tWith --stm-disable: minimise N slices per kernel launch (default = %i)\n", batch);
     printf("    [--gpus=N]\t\t\t\tWith --stm-disable and --batch: deal every batch to N devices (starting at --device),\n");
     printf("              \t\t\t\tone launch per device and one NCCL all-gather of the per-slice flow (default = %i)\n", gpus);
+    printf("    [--optimizer=rolling|local]\tPer-slice optimiser: OptimizerRolling (default, what the reference tool runs) or\n");
+    printf("                               \tOptimizerLocal (contrast-driven nx, ny descent; the slice model carries -nx, -ny)\n");
     printf("    [--device=N]\t\t\tCUDA device (default = %i)\n", device);
     printf("    <file to process or \"-\" for stdin>\n");
     exit(ret);
@@ -116,6 +119,8 @@ int main(int argc, char *argv[]) {
         else if (!strncmp(argv[i], "--flow-out=", 11)) flowOutName = argv[i] + 11;
         else if (!strncmp(argv[i], "--batch=", 8)) batch = atoi(argv[i] + 8);
         else if (!strncmp(argv[i], "--gpus=", 7)) gpus = atoi(argv[i] + 7);
+        else if (!strcmp(argv[i], "--optimizer=local")) optimizer_local = true;
+        else if (!strcmp(argv[i], "--optimizer=rolling")) optimizer_local = false;
         else if (!strncmp(argv[i], "--device=", 9)) device = atoi(argv[i] + 9);
         else if (!strcmp(argv[i], "-")) {}
         else if (argv[i][0] == '-') { fprintf(stderr, "Unknown option \"%s\".\n", argv[i]); usage(1); }
@@ -148,6 +153,10 @@ int main(int argc, char *argv[]) {
     estimator.set_scale(scale);
     estimator.set_batch(batch);
     estimator.set_gpus(gpus);
+    if (optimizer_local) {
+        if (scale > 3) { fprintf(stderr, "--optimizer=local supports --scale=1 or 3.\n"); return 1; }
+        estimator.set_optimizer_local(true);
+    }
     estimator.set_quiet(quiet);
     std::ofstream flow_out;
     if (flowOutName != NULL) {

@@ -172,6 +172,26 @@ int bf_minimize(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const i
                 const uint8_t *noise, int n, int scale, int max_iter, const bf_model *init,
                 bf_slice_result *out, double *pr_x, double *pr_y, double *nx, double *ny);
 
+/* ---- OptimizerLocal: the contrast-driven (nx, ny) descent ------------------------------------
+ * Replaces OptimizerLocal(LinearEventCloud*, scale)::run() (include/better_flow/optimizer_sampler.h:41-56,
+ * src/optimizer_sampler.cpp:4-38): per step every event is projected with the global (nx, ny)
+ * (Event::project, event.h:65-70), splatted into a saturating 8-bit count image, the image is
+ * Gaussian-blurred (scale x scale) and scored by the mean of its non-zero pixels; nx, ny are moved
+ * alternately by +-dn, dn halving and flipping whenever the score does not improve, until
+ * hypot(dnx, dny) <= dn_th.  Runs in the same persistent launch as the rolling slices of a batch.
+ * t_ns is Event::t as the caller has it (the class never calls set_local_time).  scale: 1 or 3.
+ * Result record (bf_slice_result) of such a slice:
+ *   model.total_dx = nx, model.total_dy = ny      (get_nx / get_ny)
+ *   model.dx = last_score, model.dy = dnx, model.rot = dny, model.div = dn_th
+ *   model.cnt = non-zero pixels of the last image, iters = iteration_steps executed
+ *   rc = 0 ok / BF_RC_SKIPPED window too small (run() returns 1, optimizer_sampler.cpp:9-13) */
+int bf_batch_add_local(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, int n, int scale);
+/* Switch an already added slice between OptimizerRolling (0) and OptimizerLocal (1) mode. */
+int bf_batch_slot_mode(bf_ctx *ctx, int slot, int mode);
+/* One cloud, synchronously.  Returns rc or < 0. */
+int bf_local_minimize(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, int n, int scale,
+                      bf_slice_result *out);
+
 /* ---- stage-level entry points (the AccelLib surface; used by the kernel parity tests) ------ */
 
 /* AccelLib::get_time_img (accel_lib.h:211-217 -> 147-178): mean-timestamp image in seconds,

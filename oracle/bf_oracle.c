@@ -335,3 +335,151 @@ int bfo_minimize(int n, const uint16_t *fr_x, const uint16_t *fr_y, const int64_
     free(buf);
     return rc;
 }
+
+/* =====================================================================================================
+ * OptimizerLocal (src/optimizer_sampler.cpp, include/better_flow/optimizer_sampler.h): the contrast-
+ * driven coordinate descent over a global (nx, ny).  Never instantiated by DVS_flow / the CLI (only
+ * #included, dvs_flow.h:5), but it is the variant BASELINE.json's north-star prose describes
+ * ("scores image ... contrast, and gradient-descends over a global (dx,dy) flow"): SURVEY 8a-18 / 8f-3.
+ * Pinned against the reference's own class compiled into oracle/_ref (bf_ref_local) and the golden
+ * records minted from it; the Gaussian blur against fixtures from the real cv2.GaussianBlur.
+ * ===================================================================================================== */
+
+/* cv::GaussianBlur(img, img, Size(k,k), 0, 0) on CV_8UC1 (optimizer_sampler.cpp:147-149): OpenCV's 8-bit
+ * path with sigma <= 0 uses the binomial kernels [1 2 1]/4, [1 4 6 4 1]/16 in fixed point = the exact
+ * weighted sum rounded half up; BORDER_REFLECT_101. */
+static int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+void bfo_gaussian_blur_u8(int rows, int cols, int k, uint8_t *img) {
+    static const int w1[1] = {1}, w3[3] = {1, 2, 1}, w5[5] = {1, 4, 6, 4, 1};
+    const int *w = k == 1 ? w1 : k == 3 ? w3 : w5;
+    const int r = k / 2, shift = k == 1 ? 0 : k == 3 ? 4 : 8;
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)rows * cols);
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) {
+            int s = 0;
+            for (int d = -r; d <= r; ++d) s += w[d + r] * img[(size_t)i * cols + reflect101(j + d, cols)];
+            tmp[(size_t)i * cols + j] = s;
+        }
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) {
+            int s = 0;
+            for (int d = -r; d <= r; ++d) s += w[d + r] * tmp[(size_t)reflect101(i + d, rows) * cols + j];
+            img[(size_t)i * cols + j] = (uint8_t)((s + ((1 << shift) >> 1)) >> shift);
+        }
+    free(tmp);
+}
+
+typedef struct {
+    int n, scale;
+    const uint16_t *fr_x, *fr_y;
+    const int64_t *t;
+    int wsize_x, wsize_y, img_rows, img_cols;
+    double cpr_x, cpr_y;      /* event_c.pr_x / pr_y: event_c has t = 0, so project() leaves it at float(fr) */
+    double *pr_x, *pr_y;
+    uint8_t *img;
+    int steps;
+} local_state;
+
+/* OptimizerLocal::iteration_step (optimizer_sampler.cpp:120-153) + get_event_score (:192-204) */
+static double local_step(local_state *L, double nx, double ny) {
+    const double nz = 127;
+    const int s = L->scale;
+    for (int i = 0; i < L->n; ++i) {                                    /* :121  Event::project -> apply_project */
+        float kx = (float)nx / nz, ky = (float)ny / nz;                 /* event.h:164-165 */
+        float tf = (float)L->t[i];
+        L->pr_x[i] = (float)L->fr_x[i] - kx * tf / 10000.0;             /* event.h:167-168 */
+        L->pr_y[i] = (float)L->fr_y[i] - ky * tf / 10000.0;
+    }
+    memset(L->img, 0, (size_t)L->img_rows * L->img_cols);               /* :124 */
+    const double x_shift = -L->cpr_x * s + (double)L->wsize_x / 2.0;    /* :126-127 */
+    const double y_shift = -L->cpr_y * s + (double)L->wsize_y / 2.0;
+    for (int i = 0; i < L->n; ++i) {
+        int x = L->pr_x[i] * s + x_shift;                               /* :130-131  f64, truncation */
+        int y = L->pr_y[i] * s + y_shift;
+        if (x >= L->wsize_x || x < 0 || y >= L->wsize_y || y < 0) continue;   /* :133-134 */
+        x += s / 2;                                                     /* :136-137 */
+        y += s / 2;
+        for (int jx = x - s / 2; jx <= x + s / 2; ++jx)                 /* :139-145  saturating u8 count */
+            for (int jy = y - s / 2; jy <= y + s / 2; ++jy) {
+                uint8_t *p = L->img + (size_t)jx * L->img_cols + jy;
+                if (*p < 255) (*p)++;
+            }
+    }
+    if (s > 1) bfo_gaussian_blur_u8(L->img_rows, L->img_cols, s, L->img);   /* :147-149 */
+    L->steps++;
+    double nz_avg = 0;                                                  /* :192-204  mean of the non-zero pixels */
+    long nz_cnt = 0;
+    for (size_t k = 0; k < (size_t)L->img_rows * L->img_cols; ++k) {
+        if (L->img[k] == 0) continue;
+        nz_cnt++;
+        nz_avg += L->img[k];
+    }
+    return nz_cnt == 0 ? 0 : nz_avg / (double)nz_cnt;
+}
+
+/* OptimizerLocal(LinearEventCloud*, scale) + run() (optimizer_sampler.h:41-56, optimizer_sampler.cpp:4-38,90-117).
+ *   out10    nx, ny, last_score, dnx, dny, dn_th, metric_wsizex, metric_wsizey, scale_img_x, scale_img_y
+ *   out_img  nullable: the image of the last iteration_step;  out_pr nullable: 2n doubles pr_x, pr_y
+ * Returns run()'s value: 0 ok, 1 window too small. */
+int bfo_local_minimize(int n, const uint16_t *fr_x, const uint16_t *fr_y, const int64_t *t, int res_x, int res_y,
+                       int scale, double *out10, int *out_steps, uint8_t *out_img, double *out_pr) {
+    /* LinearEventCloud::push_back bbox (datastructures.h:141-148): starts at INT_MAX / INT_MIN */
+    int x_min = 2147483647, y_min = 2147483647, x_max = -2147483647 - 1, y_max = -2147483647 - 1;
+    for (int i = 0; i < n; ++i) {
+        if ((int)fr_x[i] > x_max) x_max = fr_x[i];
+        if ((int)fr_y[i] > y_max) y_max = fr_y[i];
+        if ((int)fr_x[i] < x_min) x_min = fr_x[i];
+        if ((int)fr_y[i] < y_min) y_min = fr_y[i];
+    }
+    local_state L;
+    memset(&L, 0, sizeof L);
+    L.n = n; L.scale = scale; L.fr_x = fr_x; L.fr_y = fr_y; L.t = t;
+    L.wsize_x = scale * (x_max - x_min);                                /* optimizer_sampler.h:48-49 */
+    L.wsize_y = scale * (y_max - y_min);
+    L.cpr_x = (float)(unsigned)((x_max - x_min) / 2 + x_min);          /* :51  Event(uint, uint, 0); pr = float(fr) */
+    L.cpr_y = (float)(unsigned)((y_max - y_min) / 2 + y_min);
+    L.img_rows = L.wsize_x + scale;                                     /* update_fields, optimizer_sampler.cpp:207-214 */
+    L.img_cols = L.wsize_y + scale;
+    double nx = 0, ny = 0, last_score = 0, dscore = 0;                  /* run(), :5-7 */
+    double dnx = 0.01, dny = 0.01;
+    const double dn_th = (127 * 1 * 1000.0) / (double)(10ULL * (unsigned long long)scale * 100000000ULL);
+    int rc = 0;
+    if (n == 0 || ((L.img_rows < scale * res_x / 15) && (L.img_cols < scale * res_y / 15))) rc = 1;   /* :9-13 */
+    if (rc == 0) {
+        L.pr_x = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        L.pr_y = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        L.img = (uint8_t *)calloc((size_t)L.img_rows * L.img_cols, 1);
+        last_score = local_step(&L, nx, ny);                            /* :16 */
+        while (hypot(dnx, dny) > dn_th) {                               /* :20 */
+            {                                                           /* compute_new_nx, :90-102 */
+                double nx_new = nx + dnx;
+                double new_score = local_step(&L, nx_new, ny);
+                dscore = new_score - last_score;
+                last_score = new_score;
+                if (dscore <= 0) dnx = -dnx / 2.0;
+                nx = nx_new;
+            }
+            {                                                           /* compute_new_ny, :105-117 */
+                double ny_new = ny + dny;
+                double new_score = local_step(&L, nx, ny_new);
+                dscore = new_score - last_score;
+                last_score = new_score;
+                if (dscore <= 0) dny = -dny / 2.0;
+                ny = ny_new;
+            }
+        }
+        if (out_img) memcpy(out_img, L.img, (size_t)L.img_rows * L.img_cols);
+        if (out_pr) { memcpy(out_pr, L.pr_x, sizeof(double) * n); memcpy(out_pr + n, L.pr_y, sizeof(double) * n); }
+        free(L.pr_x); free(L.pr_y); free(L.img);
+    }
+    if (out10) {
+        out10[0] = nx; out10[1] = ny; out10[2] = last_score; out10[3] = dnx; out10[4] = dny; out10[5] = dn_th;
+        out10[6] = L.wsize_x; out10[7] = L.wsize_y; out10[8] = L.img_rows; out10[9] = L.img_cols;
+    }
+    if (out_steps) *out_steps = L.steps;
+    return rc;
+}

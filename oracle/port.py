@@ -128,3 +128,37 @@ def minimize(fr_x, fr_y, t_ns, scale=3, max_iter=-1, init_model=None, noise=None
     if want_events:
         res["pr_x"], res["pr_y"], res["nx"], res["ny"] = pr[:n], pr[n:2 * n], pr[2 * n:3 * n], pr[3 * n:]
     return res
+
+
+def gaussian_blur_u8(img, ksize):
+    """bfo_gaussian_blur_u8: the restated cv::GaussianBlur(img, img, Size(k, k), 0, 0) for CV_8UC1."""
+    lib = load()
+    a = np.array(img, dtype=np.uint8, order="C")
+    lib.bfo_gaussian_blur_u8(C.c_int(a.shape[0]), C.c_int(a.shape[1]), C.c_int(ksize), _p(a, C.c_uint8))
+    return a
+
+
+def local_minimize(fr_x, fr_y, t_ns, scale=3, rows=180, cols=240, want_image=False, want_events=False):
+    """OptimizerLocal(cloud, scale).run() restated (optimizer_sampler.cpp)."""
+    lib = load()
+    lib.bfo_local_minimize.restype = C.c_int
+    n = int(len(fr_x))
+    fx = np.ascontiguousarray(fr_x, dtype=np.uint16)
+    fy = np.ascontiguousarray(fr_y, dtype=np.uint16)
+    t = np.ascontiguousarray(t_ns, dtype=np.int64)
+    out10 = np.zeros(10)
+    steps = C.c_int(0)
+    su = setup_slice(fx, fy, rows, cols, scale) if n else None
+    img = np.zeros((su.img_rows, su.img_cols), dtype=np.uint8) if (want_image and n) else None
+    pr = np.zeros(2 * n) if want_events else None
+    rc = lib.bfo_local_minimize(C.c_int(n), _p(fx, C.c_uint16), _p(fy, C.c_uint16), _p(t, C.c_int64), C.c_int(rows),
+                                C.c_int(cols), C.c_int(scale), _p(out10, C.c_double), C.byref(steps),
+                                _p(img, C.c_uint8), _p(pr, C.c_double))
+    res = {"rc": rc, "nx": out10[0], "ny": out10[1], "score": out10[2], "dnx": out10[3], "dny": out10[4],
+           "dn_th": out10[5], "wsize_x": int(out10[6]), "wsize_y": int(out10[7]), "img_rows": int(out10[8]),
+           "img_cols": int(out10[9]), "steps": steps.value}
+    if want_image:
+        res["image"] = img
+    if want_events:
+        res["pr_x"], res["pr_y"] = pr[:n], pr[n:]
+    return res

@@ -155,3 +155,40 @@ def stream(fr_x, fr_y, ts_ns, config=0, ev_refresh=20000, time_refresh_ns=330000
                           _p(models, C.c_double), _p(info, C.c_longlong))
     k = min(k, max_slices)
     return models[:k], info[:k]
+
+
+def blur(img, ksize, rows=180, cols=240):
+    """The cv shim's GaussianBlur stand-in (what the compiled reference's OptimizerLocal calls)."""
+    lib = load(rows, cols)
+    a = np.array(img, dtype=np.uint8, order="C")
+    lib.bf_ref_blur(C.c_int(a.shape[0]), C.c_int(a.shape[1]), C.c_int(ksize), _p(a, C.c_uint8))
+    return a
+
+
+def local_minimize(fr_x, fr_y, t_ns, scale=3, rows=180, cols=240, want_image=False, want_events=False):
+    """The reference's own OptimizerLocal(LinearEventCloud*, scale)::run() (optimizer_sampler.cpp:4-38)."""
+    lib = load(rows, cols)
+    lib.bf_ref_local.restype = C.c_int
+    n = int(len(fr_x))
+    fx = np.ascontiguousarray(fr_x, dtype=np.uint32)
+    fy = np.ascontiguousarray(fr_y, dtype=np.uint32)
+    t = np.ascontiguousarray(t_ns, dtype=np.int64)
+    out10 = np.zeros(10)
+    steps = C.c_int(0)
+    secs = C.c_double(0)
+    img = None
+    if want_image and n:
+        r = scale * (int(fx.max()) - int(fx.min())) + scale
+        c = scale * (int(fy.max()) - int(fy.min())) + scale
+        img = np.zeros((r, c), dtype=np.uint8)
+    pr = np.zeros(2 * n) if want_events else None
+    rc = lib.bf_ref_local(C.c_int(n), _p(fx, C.c_uint32), _p(fy, C.c_uint32), _p(t, C.c_int64), C.c_int(scale),
+                          _p(out10, C.c_double), C.byref(steps), _p(img, C.c_uint8), _p(pr, C.c_double), C.byref(secs))
+    res = {"rc": rc, "nx": out10[0], "ny": out10[1], "score": out10[2], "dnx": out10[3], "dny": out10[4],
+           "dn_th": out10[5], "wsize_x": int(out10[6]), "wsize_y": int(out10[7]), "img_rows": int(out10[8]),
+           "img_cols": int(out10[9]), "steps": steps.value, "seconds": secs.value}
+    if want_image:
+        res["image"] = img
+    if want_events:
+        res["pr_x"], res["pr_y"] = pr[:n], pr[n:]
+    return res

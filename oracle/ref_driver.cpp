@@ -11,7 +11,11 @@
 //                          AccelLib::Sobel_cpu       (accel_lib.h:513-543);
 //   * bf_ref_project    -- Event::project_4param_reinit (event.h:99-110);
 //   * bf_ref_stream     -- DVS_flow<50000,200ms> / <30000,70ms> fed event by event,
-//                          returning the per-slice models (dvs_flow.h:163-252).
+//                          returning the per-slice models (dvs_flow.h:163-252);
+//   * bf_ref_local      -- OptimizerLocal(LinearEventCloud*, scale)::run(), the contrast-driven
+//                          (nx, ny) coordinate descent (optimizer_sampler.cpp:4-38); its
+//                          cv::GaussianBlur is the shim's restatement (see oracle/shim);
+//   * bf_ref_blur       -- that GaussianBlur stand-in alone, for the check against real cv2.
 // The only thing the driver adds is plumbing: it builds Event objects from SoA
 // arrays, reads results out of public/protected members through a derived class,
 // and recovers run()'s iteration count from the TBB stand-in's call counter.
@@ -26,6 +30,7 @@
 #include <better_flow/object_model.h>
 #include <better_flow/accel_lib.h>
 #include <better_flow/optimizer_rolling.h>
+#include <better_flow/optimizer_sampler.h>
 #include <better_flow/dvs_flow.h>
 
 namespace {
@@ -75,6 +80,15 @@ ObjectModel model_from_array(const double *a) {
     m.total_dx = a[7]; m.total_dy = a[8]; m.total_rot = a[9]; m.total_div = a[10];
     return m;
 }
+
+struct LocalProbe : public OptimizerLocal {
+    using OptimizerLocal::OptimizerLocal;
+    void state_out(double *o) {
+        o[0] = nx; o[1] = ny; o[2] = last_score; o[3] = dnx; o[4] = dny; o[5] = dn_th;
+        o[6] = metric_wsizex; o[7] = metric_wsizey; o[8] = scale_img_x; o[9] = scale_img_y;
+    }
+    const cv::Mat &image() const { return project_img; }
+};
 
 template <class Flow> struct FlowProbe : public Flow {
     using Flow::Flow;
@@ -246,6 +260,43 @@ void bf_ref_compute_uv(int n, const double *nx, const double *ny, double *u, dou
 // config 1: DVS_flow<30000,  70 ms> (ros_nodes_src/bf_visualizer.cpp:30-34)
 // models: 11 doubles per slice; slice_info: 3 int64 per slice = {events consumed, buffer size, buffer time diff}
 // Returns number of slices computed (may exceed max_slices; only the first max_slices are stored).
+// OptimizerLocal on one cloud.  t_local[i] becomes Event::t (the class never calls set_local_time;
+// the caller's t is what Event::project uses, event.h:164-168).
+//   out10   nx, ny, last_score, dnx, dny, dn_th, metric_wsizex, metric_wsizey, scale_img_x, scale_img_y
+//   out_img nullable: the CV_8UC1 project_img of the LAST iteration_step, scale_img_x * scale_img_y bytes
+//   out_pr  nullable: 2*n doubles pr_x[n], pr_y[n] after run()
+// Returns run()'s value (0 ok, 1 window too small); *out_steps = number of iteration_steps (blur calls; -1 for scale 1).
+int bf_ref_local(int n, const uint32_t *fr_x, const uint32_t *fr_y, const int64_t *t_local, int scale,
+                 double *out10, int *out_steps, uint8_t *out_img, double *out_pr, double *out_seconds) {
+    StdoutSilencer quiet;
+    LinearEventCloud cloud;
+    for (int i = 0; i < n; ++i) {
+        Event e(fr_x[i], fr_y[i], 0);
+        e.t = t_local[i];
+        cloud.push_back(e);
+    }
+    LocalProbe opt(&cloud, scale);
+    const unsigned long long b0 = cv::bf_shim_blur_calls();
+    auto t0 = std::chrono::steady_clock::now();
+    const int rc = opt.run();
+    auto t1 = std::chrono::steady_clock::now();
+    if (out_seconds) *out_seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (out_steps) *out_steps = scale > 1 ? int(cv::bf_shim_blur_calls() - b0) : -1;
+    if (out10) opt.state_out(out10);
+    if (out_img) std::memcpy(out_img, opt.image().data, size_t(opt.image().rows) * opt.image().cols);
+    if (out_pr)
+        for (int i = 0; i < n; ++i) { out_pr[i] = cloud[i].pr_x; out_pr[n + i] = cloud[i].pr_y; }
+    return rc;
+}
+
+// The shim's cv::GaussianBlur on a CV_8UC1 image (in place), for validation against cv2.
+void bf_ref_blur(int rows, int cols, int ksize, uint8_t *img) {
+    cv::Mat m(rows, cols, CV_8UC1);
+    std::memcpy(m.data, img, size_t(rows) * cols);
+    cv::GaussianBlur(m, m, cv::Size(ksize, ksize), 0, 0);
+    std::memcpy(img, m.data, size_t(rows) * cols);
+}
+
 int bf_ref_stream(int config, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint64_t *ts,
                   unsigned long long ev_refresh, unsigned long long time_refresh_ns,
                   int scale, int max_iter, int stm_disable, int flush,

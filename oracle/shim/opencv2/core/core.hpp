@@ -14,6 +14,8 @@
 #pragma once
 
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <climits>
@@ -198,7 +200,43 @@ inline void vconcat(const Mat &, const Mat &, Mat &) {}
 inline void transpose(const Mat &, Mat &) {}
 inline void cvtColor(const Mat &, Mat &, int, int = 0) {}
 inline void resize(const Mat &, Mat &, Size, double = 0, double = 0, int = 1) {}
-inline void GaussianBlur(const Mat &, Mat &, Size, double, double = 0, int = BORDER_DEFAULT) {}
+// The one filtering call that carries arithmetic on a path we check: OptimizerLocal::iteration_step
+// blurs its CV_8UC1 event-count image with GaussianBlur(img, img, Size(scale, scale), 0, 0)
+// (optimizer_sampler.cpp:147-149).  OpenCV's 8-bit path for ksize 3 / 5 with sigma <= 0 uses the
+// binomial kernels [1 2 1]/4 and [1 4 6 4 1]/16 in fixed point, i.e. the exactly computed weighted
+// sum rounded half up, with BORDER_REFLECT_101 (the default).  tests/test_oracle_local.py checks
+// this stand-in against fixtures produced by the real cv2.GaussianBlur (oracle/make_golden_local.py).
+inline unsigned long long &bf_shim_blur_calls() {
+    static unsigned long long n = 0;
+    return n;
+}
+inline void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double, double = 0, int = BORDER_DEFAULT) {
+    ++bf_shim_blur_calls();
+    if (src.type() != CV_8UC1 || ksize.width != ksize.height || (ksize.width != 1 && ksize.width != 3 && ksize.width != 5)) {
+        std::fprintf(stderr, "cv shim: GaussianBlur supports CV_8UC1 with ksize 1, 3 or 5 only\n");
+        std::abort();
+    }
+    const int k = ksize.width, r = k / 2, R = src.rows, C = src.cols;
+    static const int w3[3] = {1, 2, 1}, w5[5] = {1, 4, 6, 4, 1}, w1[1] = {1};
+    const int *w = k == 1 ? w1 : k == 3 ? w3 : w5;
+    const int shift = k == 1 ? 0 : k == 3 ? 4 : 8;
+    auto refl = [](int i, int n) { if (n == 1) return 0; while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i; return i; };
+    std::vector<int> tmp(size_t(R) * C);
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < C; ++j) {
+            int s = 0;
+            for (int d = -r; d <= r; ++d) s += w[d + r] * int(src.data[size_t(i) * C + refl(j + d, C)]);
+            tmp[size_t(i) * C + j] = s;
+        }
+    Mat out(R, C, CV_8UC1);
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < C; ++j) {
+            int s = 0;
+            for (int d = -r; d <= r; ++d) s += w[d + r] * tmp[size_t(refl(i + d, R)) * C + j];
+            out.data[size_t(i) * C + j] = (unsigned char)((s + ((1 << shift) >> 1)) >> shift);
+        }
+    dst = out;
+}
 inline void Sobel(const Mat &, Mat &, int, int, int, int = 3, double = 1, double = 0, int = BORDER_DEFAULT) {}
 inline void Scharr(const Mat &, Mat &, int, int, int, double = 1, double = 0, int = BORDER_DEFAULT) {}
 inline void Laplacian(const Mat &, Mat &, int, int = 1, double = 1, double = 0, int = BORDER_DEFAULT) {}
