@@ -37,28 +37,36 @@ struct __align__(16) Smem {
     int minmax[6];
 };
 
+__device__ __forceinline__ void copy_cg(void *dst, const void *src, int bytes);
+
+// What the iteration loop of a rolling slice carries from one iteration to the next, besides the
+// per-slice scalars in shared memory (S.sd, S.g, S.pk, S.opt, S.proj).  A helper group enters the
+// loop of ANOTHER group's slice with a LoopState rebuilt from that group's JoinRecord.
+struct LoopState {
+    int vgroup;            // group whose slice / images / flags / partial sums / barrier are used
+    int rank, G;           // this CTA's rank among the G CTAs currently working on the slice
+    int iter, buf, n_prev;
+    unsigned tag, bar_target;
+    bool helper;
+};
+
 template <int SH>
-__device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
-                          int rank) {
-    u64 *img0 = P.images + (size_t)group * 2 * P.img_elems;
+__device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
+    GroupWs *ws = P.ws + L.vgroup;
+    u64 *img0 = P.images + (size_t)L.vgroup * 2 * P.img_elems;
     u64 *img1 = img0 + P.img_elems;
-    unsigned *flags0 = P.flags + (size_t)group * 2 * P.flag_elems;
+    unsigned *flags0 = P.flags + (size_t)L.vgroup * 2 * P.flag_elems;
     unsigned *flags1 = flags0 + P.flag_elems;
-    double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
+    double *partials = P.partials + (size_t)L.vgroup * P.part_stride * BF_NSUMS;
     const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
+    const int rank = L.rank;
+    const bool leader = !L.helper && rank == 0 && threadIdx.x == 0;
+    const bool may_grow = P.allow_help != 0;   // (earlier helpers are full members: they must follow later growth too)
 
     // per-slice cell tables live behind the fixed part of the shared-memory block
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
     fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
-    if (threadIdx.x == 0) {
-        bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
-        if (S.sd.has_init) {
-            // set_model (optimizer_rolling.h:289-299): note model.cx/cy are used as stored
-            const bf_model &m = S.sd.init;
-            bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
-        }
-    }
     __syncthreads();
 
     long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
@@ -70,42 +78,52 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         pf[slot] += now_ - tc;                \
         tc = now_;                            \
     }
-    int buf = 0;
-    int n_prev = -1;    // live cells of the previous iteration when they are still listed in S.list[buf ^ 1]
-    for (int iter = 0;; ++iter) {
+    int buf = L.buf;
+    int n_prev = L.n_prev;   // live cells of the previous iteration when they are still listed in S.list[buf ^ 1]
+    int G = L.G;
+    unsigned tag = L.tag, bar_target = L.bar_target;
+    for (int iter = L.iter;; ++iter) {
         u64 *img_new = buf ? img1 : img0;
         u64 *img_old = buf ? img0 : img1;
         unsigned *flags_new = buf ? flags1 : flags0;
         unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
-        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, iter == 0, iter > 0 || S.sd.has_init != 0, img_new, nullptr,
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, G, iter == 0, iter > 0 || S.sd.has_init != 0, img_new, nullptr,
                        flags_new, tag, row_tab, col_tab);
         if (pf) __syncthreads();
         PF_MARK(PF_EVENT);
         {
-            const long long sp = group_barrier(&ws->bar, bar_target, P.G);   // A: all splats of this iteration are in L2
+            const long long sp = group_barrier(&ws->bar, bar_target, G);   // A: all splats of this iteration are in L2
             if (prof) pf[PF_BAR_A_SPIN] += sp;
         }
         PF_MARK(PF_BAR_A);
 
         Acc acc;
         acc_zero(acc);
-        n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, P.G, S.list[buf], S.scan,
+        n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, G, S.list[buf], S.scan,
                                        nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
                                        n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
         if (pf) __syncthreads();
         PF_MARK(PF_CELLS);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
         PF_MARK(PF_REDUCE);
+        // HELPING, victim side: the leader's decision to let a claimed helper in travels with barrier B
+        // (and once the previous helper is in, the slice is opened again for the next one, up to BF_MAX_GROW groups)
+        if (leader && may_grow) {
+            const unsigned st = ld_relaxed_u32(&ws->help_state);
+            if (st == (unsigned)HELP_CLAIMED) ws->grow_iter = iter;
+            else if (st == (unsigned)HELP_JOINED && G + P.G <= BF_MAX_GROW * P.G) atomicExch(&ws->help_state, (unsigned)HELP_OPEN);
+        }
         {
-            const long long sp = group_barrier(&ws->bar, bar_target, P.G);   // B: all partial sums are visible
+            const long long sp = group_barrier(&ws->bar, bar_target, G);   // B: all partial sums are visible
             if (prof) pf[PF_BAR_B_SPIN] += sp;
         }
         PF_MARK(PF_BAR_B);
+        const bool grow = may_grow && __ldcg(&ws->grow_iter) == iter;
 
         if (threadIdx.x < 32) {
             BfSums s;
-            group_sums(s, partials, P.G, pf ? pf + 14 : nullptr);
+            group_sums(s, partials, G, pf ? pf + 14 : nullptr);
             PF_MARK(PF_SCAN);   // (slot reused: time of the partial-sum gather)
             const bool cont = opt_advance_warp(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj);
             if (threadIdx.x == 0) S.cont = cont ? 1 : 0;
@@ -115,28 +133,93 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
         if (prof) pf[PF_ITERS] += 1;
         if (!S.cont) break;
         buf ^= 1;
+        if (grow) {
+            // from the next iteration on the slice is worked on by G + P.G CTAs: ranks G .. G + P.G - 1 are the new helpers
+            if (leader) {
+                JoinRecord &r = P.join[L.vgroup];
+                r.sd = S.sd; r.g = S.g; r.pk = S.pk; r.opt = S.opt; r.proj = S.proj;
+                r.slice = S.sd.n;   // (informational)
+                r.iter_next = iter + 1; r.buf = buf; r.tag = tag; r.bar_target = bar_target;
+                r.G_new = G + P.G; r.rank_base = G;
+                __threadfence();
+                red_release_add_u32(&ws->join_seq, 1u);
+                atomicExch(&ws->help_state, (unsigned)HELP_JOINED);
+            }
+            G = G + P.G;
+            // event chunks are re-dealt among the larger group: drop L1 lines of neighbouring chunks' states this SM may hold
+            if (threadIdx.x == 0) fence_acq_rel_gpu();
+            __syncthreads();
+        }
     }
     // Zero the cells of the image that is still live (its readers all passed barrier B; the next
     // slice's first splat comes two group barriers later).
     {
         Acc none;
-        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, S.rcp_tab, nullptr, 0u, rank, P.G, S.list[buf ^ 1], S.scan, nullptr,
+        image_pass<SH, false>(none, nullptr, P.pitch, S.g, S.pk, S.rcp_tab, nullptr, 0u, rank, G, S.list[buf ^ 1], S.scan, nullptr,
                               nullptr, nullptr, buf ? img1 : img0, buf ? flags1 : flags0, tag,
                               n_prev >= 0 ? S.list[buf] : nullptr, n_prev);
     }
     // Last re-projection of iteration_step (optimizer_rolling.h:340-344): only needed when the caller
     // wants the per-event state back (writeout_events).
     if (P.want_events)
-        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, false, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
+        event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, G, false, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
     if (pf) __syncthreads();
     PF_MARK(PF_FINAL);
-    if (prof) pf[PF_SLICES] += 1;
+    if (prof && !L.helper) pf[PF_SLICES] += 1;
 #undef PF_MARK
+    L.tag = tag; L.bar_target = bar_target; L.G = G;
+}
+
+// OptimizerRolling::run for the slice in S.sd, owned by this CTA's group.
+template <int SH>
+__device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
+                          int rank) {
+    if (threadIdx.x == 0) {
+        bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
+        if (S.sd.has_init) {
+            // set_model (optimizer_rolling.h:289-299): note model.cx/cy are used as stored
+            const bf_model &m = S.sd.init;
+            bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
+        }
+        if (P.allow_help && rank == 0) {
+            ws->grow_iter = -1;
+            __threadfence();
+            atomicExch(&ws->help_state, (unsigned)HELP_OPEN);
+        }
+    }
+    LoopState L;
+    L.vgroup = group; L.rank = rank; L.G = P.G; L.iter = 0; L.buf = 0; L.n_prev = -1;
+    L.tag = tag; L.bar_target = bar_target; L.helper = false;
+    slice_loop<SH>(P, S, L);
+    tag = L.tag; bar_target = L.bar_target;
+    // the slice is over: nobody can join any more (a helper that had claimed but not joined sees 0 and leaves)
+    if (P.allow_help && rank == 0 && threadIdx.x == 0) atomicExch(&ws->help_state, (unsigned)HELP_CLOSED);
+}
+
+// HELPING, helper side: join the slice group `v` is minimising (its leader has published P.join[v]).
+template <int SH>
+__device__ void help_slice(const KParams &P, Smem &S, int v, int my_rank) {
+    const JoinRecord &r = P.join[v];
+    if (threadIdx.x == 0) {
+        copy_cg(&S.sd, &r.sd, (int)sizeof(SliceDesc));
+        copy_cg(&S.g, &r.g, (int)sizeof(BfGeom));
+        copy_cg(&S.pk, &r.pk, (int)sizeof(BfPack));
+        copy_cg(&S.opt, &r.opt, (int)sizeof(BfOpt));
+        copy_cg(&S.proj, &r.proj, (int)sizeof(BfProj));
+    }
+    __syncthreads();   // slice_loop reads S.g right away
+    LoopState L;
+    L.vgroup = v; L.rank = __ldcg(&r.rank_base) + my_rank; L.G = __ldcg(&r.G_new);
+    L.iter = __ldcg(&r.iter_next); L.buf = __ldcg(&r.buf); L.n_prev = -1;
+    L.tag = __ldcg(&r.tag); L.bar_target = __ldcg(&r.bar_target); L.helper = true;
+    slice_loop<SH>(P, S, L);   // (its leading __syncthreads publishes the shared-memory copy to the CTA)
 }
 
 // OptimizerLocal::run (optimizer_sampler.cpp:4-38) for the slice in S.sd: same double-buffered
 // event pass -> barrier -> image pass -> barrier -> control step cycle as run_slice, one cycle per
 // iteration_step.
+__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank);
+
 template <int SH>
 __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
                                 int rank) {
@@ -144,7 +227,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
     u64 *img1 = img0 + P.img_elems;
     unsigned *flags0 = P.flags + (size_t)group * 2 * P.flag_elems;
     unsigned *flags1 = flags0 + P.flag_elems;
-    double *partials = P.partials + (size_t)group * P.G * BF_NSUMS;
+    double *partials = P.partials + (size_t)group * P.part_stride * BF_NSUMS;
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
     fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
@@ -158,7 +241,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
         unsigned *flags_new = buf ? flags1 : flags0;
         unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
-        local_event_pass<SH>(P, S.sd, S.g, S.pk, S.lopt.cur_nx, S.lopt.cur_ny, rank, img_new, flags_new, tag, row_tab, col_tab);
+        local_event_pass<SH>(P, S.sd, S.g, S.pk, S.lopt.cur_nx, S.lopt.cur_ny, rank, P.G, img_new, flags_new, tag, row_tab, col_tab);
         group_barrier(&ws->bar, bar_target, P.G);
         Acc acc;
         acc_zero(acc);
@@ -194,6 +277,74 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
     __syncthreads();
 }
 
+// Copy `bytes` (a multiple of 8) from global memory through L2 only (the source was written by another SM).
+__device__ __forceinline__ void copy_cg(void *dst, const void *src, int bytes) {
+    const long long *s8 = reinterpret_cast<const long long *>(src);
+    long long *d8 = reinterpret_cast<long long *>(dst);
+    for (int k = 0; k < bytes / 8; ++k) d8[k] = __ldcg(s8 + k);
+}
+
+// HELPING, helper side (see bf_device.cuh).  Entered by a group that found the slice queue empty.
+__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank) {
+    const int n_groups = (int)gridDim.x / P.G;
+    if (rank == 0 && threadIdx.x == 0) atomicAdd(P.groups_done, 1u);
+    for (;;) {
+        // ---- the group's leader claims a victim (or learns that every group is out of slices)
+        if (rank == 0 && threadIdx.x == 0) {
+            int v = -1;
+            unsigned seq = 0;
+            for (;;) {
+                for (int k = 1; k < n_groups && v < 0; ++k) {
+                    const int g2 = (group + k) % n_groups;
+                    GroupWs *w = P.ws + g2;
+                    if (ld_relaxed_u32(&w->help_state) != (unsigned)HELP_OPEN) continue;
+                    const unsigned sq = ld_relaxed_u32(&w->join_seq);   // sampled BEFORE the claim
+                    if (atomicCAS(&w->help_state, (unsigned)HELP_OPEN, (unsigned)HELP_CLAIMED) == (unsigned)HELP_OPEN) { v = g2; seq = sq; }
+                }
+                if (v >= 0 || ld_relaxed_u32(P.groups_done) >= (unsigned)n_groups) break;
+                __nanosleep(2000);
+            }
+            ws->victim = v;
+            ws->victim_seq = seq;
+        }
+        group_barrier(&ws->bar, bar_target, P.G);
+        const int v = __ldcg(&ws->victim);
+        if (v < 0) return;
+        const unsigned seq0 = __ldcg(&ws->victim_seq);
+        // ---- every CTA of the helper group waits for the victim's verdict: joined, or slice over
+        if (threadIdx.x == 0) {
+            GroupWs *w = P.ws + v;
+            int joined = 0;
+            for (;;) {
+                if (ld_relaxed_u32(&w->join_seq) != seq0) { joined = 1; break; }
+                const unsigned st = ld_relaxed_u32(&w->help_state);
+                if (st == (unsigned)HELP_CLOSED || st == (unsigned)HELP_OPEN) {
+                    // over -- unless the record was published and the slice then finished with us still
+                    // polling, which cannot happen (the victim waits for us at its next barrier); re-check anyway
+                    fence_acq_rel_gpu();
+                    joined = ld_relaxed_u32(&w->join_seq) != seq0 ? 1 : 0;
+                    break;
+                }
+                __nanosleep(200);
+            }
+            if (joined) fence_acq_rel_gpu();   // acquire the JoinRecord
+            S.cont = joined;
+        }
+        __syncthreads();
+        const int joined = S.cont;
+        __syncthreads();
+        if (joined) {
+            const int scale = __ldcg(&P.join[v].sd.scale);
+            switch (scale) {
+                case 1: help_slice<0>(P, S, v, rank); break;
+                case 3: help_slice<1>(P, S, v, rank); break;
+                default: help_slice<2>(P, S, v, rank); break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
 // (twice the warps to hide L2 latency, at the price of a few spills).
 template <int MINB>
@@ -225,7 +376,11 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
         }
         group_barrier(&ws->bar, bar_target, P.G);
         const int slice = __ldcg(&ws->cur_slice);
-        if (slice >= P.n_slices) break;
+        if (slice >= P.n_slices) {
+            if (!P.allow_help) break;
+            help_phase(P, S, ws, bar_target, group, rank);   // HELPING, helper side: returns when nothing is left to help
+            break;
+        }
         if (threadIdx.x == 0) {
             S.sd = P.slices[slice];
             S.minmax[0] = INT_MAX; S.minmax[1] = INT_MIN; S.minmax[2] = INT_MAX;
@@ -312,11 +467,11 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
                 bf_make_proj(S.proj, -m.total_dx, -m.total_dy, m.cx, m.cy, m.total_div, -m.total_rot);
             }
             __syncthreads();
-            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, true, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
+            event_pass<0>(P, S.sd, S.g, S.pk, S.proj, rank, P.G, true, true, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
         } else if (guard != 0 && P.want_events) {
             BfProj none;
             none.dnx = none.dny = none.cx = none.cy = none.div = none.s = 0; none.c = 1;
-            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, true, false, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
+            event_pass<0>(P, S.sd, S.g, S.pk, none, rank, P.G, true, false, nullptr, P.nxy, nullptr, 0u, nullptr, nullptr);
         }
         __syncthreads();
 
@@ -524,6 +679,7 @@ struct bf_ctx {
     int n_groups_alloc = 0;
     int iter_cap = 20000;
     int min_events = 1000;
+    int tail_help = 1;          // idle groups join slices that are still running when the queue is empty
 
     // geometry of the stored images
     int pitch = 0, rows_alloc = 0;
@@ -546,6 +702,7 @@ struct bf_ctx {
     unsigned char *d_ctrl = nullptr;   // [queue (256 B)][GroupWs x n_groups]
     size_t ctrl_bytes = 0;
     double *d_partials = nullptr;
+    JoinRecord *d_join = nullptr;
     u64 *d_images = nullptr;
     size_t images_bytes = 0;
     unsigned *d_flags = nullptr;
@@ -629,7 +786,8 @@ static int configure(bf_ctx *c, int n_slices) {
         if (c->d_ctrl) cudaFree(c->d_ctrl);
         if (c->d_partials) cudaFree(c->d_partials);
         if (c->d_flags) cudaFree(c->d_flags);
-        c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr; c->d_flags = nullptr;
+        if (c->d_join) cudaFree(c->d_join);
+        c->d_images = nullptr; c->d_ctrl = nullptr; c->d_partials = nullptr; c->d_flags = nullptr; c->d_join = nullptr;
         c->n_groups_alloc = want;
         c->images_bytes = (size_t)want * 2 * (size_t)c->img_elems * sizeof(u64);
         CU(cudaMalloc(&c->d_images, c->images_bytes));
@@ -640,7 +798,9 @@ static int configure(bf_ctx *c, int n_slices) {
         c->ctrl_bytes = 256 + (size_t)want * sizeof(GroupWs);
         CU(cudaMalloc(&c->d_ctrl, c->ctrl_bytes));
         // one partial record per CTA slot, whatever the grouping
-        CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 4 * BF_NSUMS * sizeof(double)));
+        // one record per CTA slot, times BF_MAX_GROW: a helped slice is worked on by up to BF_MAX_GROW groups
+        CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 4 * BF_MAX_GROW * BF_NSUMS * sizeof(double)));
+        CU(cudaMalloc(&c->d_join, (size_t)want * sizeof(JoinRecord)));
     }
     pick_launch(c, n_slices, &c->G, &c->n_groups);
     return BF_OK;
@@ -747,7 +907,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
     cudaFree(c->d_events); cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy); cudaFree(c->d_slices);
     cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
-    cudaFree(c->d_stage); cudaFree(c->d_prof);
+    cudaFree(c->d_stage); cudaFree(c->d_prof); cudaFree(c->d_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -766,6 +926,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "min_group")) c->min_group = (int)std::max(1LL, value);
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
+    else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
     else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
     else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = (value >= 4 && BF_NT <= 256) ? 4 : (value >= 2 ? 2 : 1);
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
@@ -779,6 +940,7 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!strcmp(key, "min_group")) return c->min_group;
     if (!strcmp(key, "image_budget_mb")) return c->image_budget_mb;
     if (!strcmp(key, "iter_cap")) return c->iter_cap;
+    if (!strcmp(key, "tail_help")) return c->tail_help;
     if (!strcmp(key, "min_events")) return c->min_events;
     if (!strcmp(key, "sms")) return c->sms;
     if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;
@@ -980,6 +1142,10 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
     P.ready = ready;
     P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
+    P.allow_help = (c->tail_help && c->n_groups > 1) ? 1 : 0;
+    P.part_stride = P.allow_help ? BF_MAX_GROW * c->G : c->G;
+    P.join = c->d_join;
+    P.groups_done = reinterpret_cast<unsigned *>(c->d_ctrl + 128);
     P.prof = nullptr;
     if (c->profile) {
         if (!c->d_prof) CU(cudaMalloc(&c->d_prof, (size_t)1024 * BF_NPROF * sizeof(long long)));
@@ -1244,3 +1410,6 @@ int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, con
 static_assert(sizeof(bf_model) == 88, "bf_model must mirror ObjectModel's 11 scalars");
 static_assert(sizeof(bf_slice_result) == 160, "bf_slice_result layout is part of the ABI");
 static_assert(sizeof(bf_event) == 8, "bf_event is the 8-byte compact record");
+static_assert(sizeof(GroupWs) == 256, "one 256-byte control record per group");
+static_assert(sizeof(SliceDesc) % 8 == 0 && sizeof(BfGeom) % 8 == 0 && sizeof(BfPack) % 8 == 0 && sizeof(BfOpt) % 8 == 0 &&
+              sizeof(BfProj) % 8 == 0, "JoinRecord members are copied as 8-byte words");

@@ -68,9 +68,44 @@ struct GroupWs {
     unsigned bar;            // monotonically increasing arrival counter
     unsigned pad0[31];
     int cur_slice;
-    int pad1[3];
+    int victim;              // helper side: group this group is about to help (broadcast inside the helper group)
+    unsigned victim_seq;     //              value of the victim's join_seq when it was claimed
+    int pad1[1];
     int bbox[2][8];          // [parity]: x_min, x_max, y_min, y_max, t_min, t_max
-    int pad2[12];
+    // ---- tail helping (see HELPING below) ----
+    unsigned help_state;     // HELP_*: written by the group's leader and by the claiming helper (CAS)
+    unsigned join_seq;       // bumped (release) by the leader when a JoinRecord has been published
+    int grow_iter;           // iteration whose barrier B carried the leader's decision to grow
+    int pad2[9];
+};
+
+// HELPING.  Iteration counts per slice vary several-fold, so when the slice queue runs dry some
+// groups are still in the middle of a long slice while most SMs idle (16-19 % of the SM-time on the
+// benchmark batch).  A group that finds the queue empty therefore does not exit: it claims a group
+// that is still minimising (CAS on help_state) and JOINS it at an iteration boundary -- the slice is
+// then worked on by more CTAs.  All cross-iteration state of a slice lives in global memory (events,
+// states, images, flags), so joining only needs the few hundred bytes of per-slice scalars, which
+// the victim's leader publishes in a JoinRecord.  Protocol (leader = rank 0, thread 0 of the victim):
+//   helper : state 1 -> 2 by CAS, then polls join_seq (joined) / help_state (0: slice ended, give up);
+//   victim : leader samples help_state before barrier B of iteration k; if it is 2 it stores
+//            grow_iter = k (visible to the whole group after barrier B); if the GD step then says
+//            "continue", every member switches to G + G_base CTAs from iteration k+1 on and the leader
+//            publishes the record; otherwise the slice ends and help_state = 0 releases the helper.
+// Helpers join one group at a time (the leader re-opens the slice once the previous helper is in), up
+// to BF_MAX_GROW groups per slice.  Only OptimizerRolling slices are helped.
+enum { HELP_CLOSED = 0, HELP_OPEN = 1, HELP_CLAIMED = 2, HELP_JOINED = 3 };
+#define BF_MAX_GROW 8          // a slice is worked on by at most this many groups
+
+struct JoinRecord {
+    SliceDesc sd;
+    BfGeom g;
+    BfPack pk;
+    BfOpt opt;
+    BfProj proj;
+    int slice;
+    int iter_next, buf;
+    unsigned tag, bar_target;
+    int G_new, rank_base;
 };
 
 struct KParams {
@@ -96,6 +131,10 @@ struct KParams {
     int iter_cap;
     int want_events;
     int tab_rows, tab_cols;  // capacity of the per-slice cell tables in dynamic shared memory (max image rows / cols)
+    int allow_help;          // tail helping enabled (needs BF_MAX_GROW x G partial-sum slots per group)
+    int part_stride;         // partial-sum records per group (G, or BF_MAX_GROW x G with helping)
+    JoinRecord *join;        // [n_groups]
+    unsigned *groups_done;   // groups that found the slice queue empty
     const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)
     long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
 };
@@ -117,6 +156,12 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// The per-event splat: a fire-and-forget 64-bit reduction.  Written as PTX because the compiler only
+// turns an atomicAdd whose result is unused into RED when the kernel contains no fences (with the
+// helping protocol's fences it emitted the returning ATOMG form: +65 % event-pass time, measured).
+__device__ __forceinline__ void red_add_u64(u64 *p, u64 v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ld_nc_u32x4(const void *p) {
     uint4 v;
@@ -321,17 +366,17 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 &st
     if (nxy_slot != nullptr) *nxy_slot = make_double2(ex, ey);
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
-        atomicAdd(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
+        red_add_u64(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
         mark_cells_tab(c.flags, c.tag, x, y, c.row_tab, c.col_tab);
     }
 }
 
 template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
-                           const BfProj &q, int rank, bool first, bool project, u64 *img_new,
+                           const BfProj &q, int rank, int G, bool first, bool project, u64 *img_new,
                            double2 *out_nxy, unsigned *flags, unsigned tag, const int2 *row_tab, const short2 *col_tab) {
     typedef CellCfg<SH> C;
-    const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
+    const int per = (((sd.n + G - 1) / G) + 31) & ~31;
     const int lo = rank * per;
     const int cnt = min(sd.n, lo + per) - lo;
     if (cnt <= 0) return;
@@ -357,7 +402,11 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     float4 st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (p < p1) {
         e = ld_nc_u32x4(ev4 + p);
-        if (!first) st = st4[p];
+#ifdef BF_STATE_CG
+        if (!first) st = __ldcg(st4 + p);
+#else
+        if (!first) st = st4[p];   // (when a group grows -- helping -- its members invalidate L1 first, see slice_loop)
+#endif
     }
     for (; p < p1; p += BF_NT) {
         const long long np = p + BF_NT;
@@ -365,7 +414,11 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         float4 nst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (np < p1) {
             ne = ld_nc_u32x4(ev4 + np);
+#ifdef BF_STATE_CG
+            if (!first) nst = __ldcg(st4 + np);
+#else
             if (!first) nst = st4[np];
+#endif
         }
         const long long i0 = 2 * p, i1 = i0 + 1;
         const bool v0 = i0 >= gs, v1 = i1 < ge;                  // (i0 < ge and i1 >= gs hold by construction)
@@ -634,6 +687,14 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
     const bool one_chunk = n_cells <= BF_LIST_CAP;
     int n_live = -1;
     for (int base = 0; base < n_cells; base += BF_LIST_CAP) {
+        // (clearing first: it may borrow `list`, which must hold the CURRENT live cells when this returns)
+        if (img_clear != nullptr && !(one_chunk && list_prev != nullptr)) {
+            const int total = compact_cells(flags_clear, tag_clear, base, n_cells, list, scan);
+            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                const int c = base + (int)list[k];
+                cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
+            }
+        }
         if (img != nullptr) {
             const int total = compact_cells(flags, tag, base, n_cells, list, scan);
             if (one_chunk) n_live = total;
@@ -655,13 +716,6 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
                     const int ci = c / n_cj, cj = c - ci * n_cj;
                     cell_process<SH, MATERIALISE, false>(acc, img, pitch, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
                 }
-            }
-        }
-        if (img_clear != nullptr && !(one_chunk && list_prev != nullptr)) {
-            const int total = compact_cells(flags_clear, tag_clear, base, n_cells, list, scan);
-            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
-                const int c = base + (int)list[k];
-                cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
             }
         }
     }
@@ -788,9 +842,9 @@ __device__ __forceinline__ bool local_opt_advance(LocalOpt &o, double cnt, doubl
 // ints before the + scale/2 (:133-137), point splat.  No per-event state: the warp is absolute.
 template <int SH>
 __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk, double nx,
-                                 double ny, int rank, u64 *img_new, unsigned *flags, unsigned tag, const int2 *row_tab,
+                                 double ny, int rank, int G, u64 *img_new, unsigned *flags, unsigned tag, const int2 *row_tab,
                                  const short2 *col_tab) {
-    const int per = (((sd.n + P.G - 1) / P.G) + 31) & ~31;
+    const int per = (((sd.n + G - 1) / G) + 31) & ~31;
     const int lo = rank * per;
     const int cnt = min(sd.n, lo + per) - lo;
     if (cnt <= 0) return;
@@ -816,7 +870,7 @@ __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const Bf
         if ((unsigned)x < (unsigned)g.w && (unsigned)y < (unsigned)g.h) {         // :133-134
             const int xc = x + g.half, yc = y + g.half;                           // :136-137
             const u64 dt = (u64)((long long)t - (long long)pk.t_min);
-            atomicAdd(img_new + pixel_offset(xc, yc, P.pitch), one + (dt >> pk.q));
+            red_add_u64(img_new + pixel_offset(xc, yc, P.pitch), one + (dt >> pk.q));
             mark_cells_tab(flags, tag, xc, yc, row_tab, col_tab);
         }
     }

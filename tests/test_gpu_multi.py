@@ -100,3 +100,33 @@ def test_cli_gpus_flag_equals_single_gpu(tmp_path):
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append((open(out).read(), open(tmp_path / ("uv%d.txt" % gpus)).read()))
     assert outs[0] == outs[1] and len(outs[0][0].splitlines()) >= 8
+
+
+def test_tail_helping_is_result_neutral_and_engages():
+    """When the slice queue runs dry, idle groups join slices that are still being minimised (the slice is
+    then worked on by 2G CTAs).  Partial sums are combined in a different order, so results may differ in
+    the last bits of the fp64 reductions but iteration counts, dividers and the flow (to 1e-12) must not."""
+    st = synth.make_stream(240, 180, 3.0e6, 0.01 * 330, seed=31)
+    sls = synth.cut_slices(st, 0.01)[:330]
+    out = {}
+    for help_on in (0, 1):
+        ctx = bf.Context(180, 240, 3, max_events=len(st) + 64, max_slices=len(sls) + 1, device=0)
+        try:
+            ctx.set_option("tail_help", help_on)
+            for s in sls:
+                ctx.add(s.fr_x, s.fr_y, s.t_ns, 3, -1)
+            ctx.run(want_events=True)
+            res = ctx.results()
+            ev = ctx.events(len(sls) - 1, len(sls[-1].fr_x))
+            ctx.run()                                # and again: the images must have been left all-zero
+            res2 = ctx.results()
+            out[help_on] = (res, ev, res2)
+        finally:
+            ctx.close()
+    a, b = out[0], out[1]
+    for x, y, y2 in zip(a[0], b[0], b[2]):
+        assert x["rc"] == y["rc"] == 0 and x["iters"] == y["iters"] == y2["iters"]
+        assert x["dividers"].tobytes() == y["dividers"].tobytes()
+        assert np.allclose(x["model"][7:11], y["model"][7:11], rtol=1e-12, atol=0)
+        assert y["model"].tobytes() == y2["model"].tobytes() or np.allclose(y["model"], y2["model"], rtol=1e-12)
+    assert np.allclose(a[1]["pr_x"], b[1]["pr_x"], rtol=0, atol=1e-9)

@@ -13,6 +13,9 @@ sls = synth.cut_slices(st, ss)
 ctx = bf.Context(rows, cols, 3, max_events=len(st) + 1024, max_slices=len(sls) + 1, device=0)
 ctx.set_option("ctas_per_sm", int(os.environ.get("BF_CPS", "2")))
 ctx.set_option("group_size", G)
+if os.environ.get("BF_TAILHELP") is not None:
+    try: ctx.set_option("tail_help", int(os.environ["BF_TAILHELP"]))
+    except Exception: pass
 for s in sls: ctx.add(s.fr_x, s.fr_y, s.t_ns, 3, mi)
 ctx.run()
 ms = ctx.time_launches(reps) / reps
@@ -22,6 +25,10 @@ P = res[0]["img_rows"] * res[0]["img_cols"]
 alg = sum(r["iters"] * (40 * r["n_events"] + 16 * P) for r in res)
 print("slice %.3f mi %d n_slices %d G %d groups %d: %.3f ms/launch -> %.1f Mev/s, iters mean %.1f max %d, alg GB/s %.1f" % (
     ss, mi, len(sls), ctx.get_option("group_size"), ctx.get_option("n_groups"), ms, nev / ms / 1e3, np.mean(its), max(its), alg / ms / 1e6))
+
+if os.environ.get("BF_DUMP_ITERS"):
+    import json
+    json.dump({"iters": its, "n": [r["n_events"] for r in res]}, open(os.environ["BF_DUMP_ITERS"], "w"))
 
 if os.environ.get("BF_PROFILE"):
     ctx.set_option("profile", 1)
@@ -34,3 +41,5 @@ if os.environ.get("BF_PROFILE"):
         if nm in ("iters", "slices"): print("  %-10s %10.1f" % (nm, pf[:, k].mean())); continue
         print("  %-10s %12.0f  %5.1f%%   per-iter %8.0f cyc" % (nm, pf[:, k].mean(), 100 * pf[:, k].mean() / tot, pf[:, k].mean() / max(pf[:, 9].mean(), 1)))
     print("  CTA totals min/max cycles: %.0f / %.0f" % (pf[:, 13].min(), pf[:, 13].max()))
+    if os.environ.get("BF_DUMP_ITERS"):
+        np.save(os.environ["BF_DUMP_ITERS"] + ".pf.npy", pf)
