@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slices", type=int, default=SLICES_PER_STEP)
     ap.add_argument("--group-size", type=int, default=0)
+    ap.add_argument("--upload-chunks", type=int, default=0, help="chunks of the streamed event upload (0 = library default)")
     ap.add_argument("--cpu-sample", type=int, default=24, help="slices timed on the CPU baseline (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -200,6 +201,8 @@ def main():
                      device=local_rank)
     if args.group_size:
         ctx.set_option("group_size", args.group_size)
+    if args.upload_chunks:
+        ctx.set_option("upload_chunks", args.upload_chunks)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 

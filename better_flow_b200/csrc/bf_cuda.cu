@@ -668,7 +668,7 @@ struct bf_ctx {
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
     unsigned *d_ready = nullptr;          // slices uploaded so far (device), fed from h_ready (pinned)
     unsigned *h_ready = nullptr;
-    int upload_chunks = 8;
+    int upload_chunks = 32;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // options

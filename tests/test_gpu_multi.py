@@ -130,3 +130,40 @@ def test_tail_helping_is_result_neutral_and_engages():
         assert np.allclose(x["model"][7:11], y["model"][7:11], rtol=1e-12, atol=0)
         assert y["model"].tobytes() == y2["model"].tobytes() or np.allclose(y["model"], y2["model"], rtol=1e-12)
     assert np.allclose(a[1]["pr_x"], b[1]["pr_x"], rtol=0, atol=1e-9)
+
+
+def test_tail_helping_with_big_grids_warm_starts_scales_and_event_readback(oracle_port):
+    """Helping across everything a slice can carry: a 640x480 sensor (cell grid larger than one list
+    chunk, so clearing goes through the flag re-scan), scales 1/3/5 in one batch, warm-started slices,
+    per-event read-back -- and more groups than slices, so helpers join from the first iterations on.
+    Every slice must equal its own single-slice run (where nobody can help) and the exact-sum oracle."""
+    st = synth.make_stream(640, 480, 4.0e6, 0.05, seed=37)
+    sls = synth.cut_slices(st, 0.005)[:10]
+    ctx = bf.Context(480, 640, 5, max_events=len(st) + 64, max_slices=16, device=0)
+    try:
+        init = np.array([240.0, 320.0, 0, 0, 0, 0, 0, 0.01, -0.02, 1e-5, -2e-5])
+        cfg = [((1, 3, 5)[k % 3], 6 + k, init if k % 4 == 3 else None) for k in range(len(sls))]
+        singles = []
+        for s, (scale, mi, ini) in zip(sls, cfg):
+            singles.append(ctx.minimize(s.fr_x, s.fr_y, s.t_ns, scale, mi, init=ini, want_events=True))
+        ctx.set_option("group_size", 2)          # 148 groups for 10 slices: 138 groups start as helpers
+        ctx.reset()
+        for s, (scale, mi, ini) in zip(sls, cfg):
+            ctx.add(s.fr_x, s.fr_y, s.t_ns, scale, mi, init=ini)
+        ctx.run(want_events=True)
+        for k, (s, (scale, mi, ini), want) in enumerate(zip(sls, cfg, singles)):
+            got = ctx.result(k)
+            assert got["rc"] == want["rc"] == 0 and got["iters"] == want["iters"]
+            assert np.allclose(got["model"][7:11], want["model"][7:11], rtol=1e-11, atol=0)
+            ev = ctx.events(k, len(s.fr_x))
+            assert np.allclose(ev["pr_x"], want["pr_x"], rtol=0, atol=1e-9) and np.allclose(ev["nx"], want["nx"], rtol=0, atol=1e-12)
+            if k < 3:
+                ex = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=scale, max_iter=mi, init_model=ini, rows=480, cols=640,
+                                          accum_mode=1)
+                assert ex["iters"] == got["iters"]
+                assert np.allclose(got["model"][7:11], ex["model"][7:11], rtol=1e-9, atol=0)
+        ctx.run()                                  # images were left all-zero: same answers again
+        for k, want in enumerate(singles):
+            assert ctx.result(k)["iters"] == want["iters"]
+    finally:
+        ctx.close()
