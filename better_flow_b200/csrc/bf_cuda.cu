@@ -121,9 +121,12 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
         PF_MARK(PF_BAR_B);
         const bool grow = may_grow && __ldcg(&ws->grow_iter) == iter;
 
+        const bool block_gather = G >= BF_BLOCK_GATHER_MIN && G <= BF_NT;
+        if (block_gather) group_sums_block_gather(partials, G, S.red);
         if (threadIdx.x < 32) {
             BfSums s;
-            group_sums(s, partials, G, pf ? pf + 14 : nullptr);
+            if (block_gather) group_sums_block_finish(s, S.red);
+            else group_sums(s, partials, G, pf ? pf + 14 : nullptr);
             PF_MARK(PF_SCAN);   // (slot reused: time of the partial-sum gather)
             const bool cont = opt_advance_warp(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj);
             if (threadIdx.x == 0) S.cont = cont ? 1 : 0;
@@ -250,9 +253,12 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
                                           n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
         group_barrier(&ws->bar, bar_target, P.G);
+        const bool block_gather = P.G >= BF_BLOCK_GATHER_MIN && P.G <= BF_NT;
+        if (block_gather) group_sums_block_gather(partials, P.G, S.red);
         if (threadIdx.x < 32) {
             BfSums s;
-            group_sums(s, partials, P.G);
+            if (block_gather) group_sums_block_finish(s, S.red);
+            else group_sums(s, partials, P.G);
             if (threadIdx.x == 0) S.cont = local_opt_advance(S.lopt, s.cnt, s.si, P.iter_cap) ? 1 : 0;
         }
         __syncthreads();
@@ -762,6 +768,15 @@ static void pick_launch(bf_ctx *c, int n_slices, int *G, int *n_groups) {
     if (c->opt_group <= 0) groups = std::min(groups, std::max(1, n_slices));
     int g = std::max(1, slots / groups);
     if (c->opt_group > 0) g = std::min(slots, std::max(c->opt_group, g));
+    else {
+        // A small batch does not profit from every CTA: each iteration pays two barriers over the G CTAs of
+        // a group and one record per CTA in the reduction, so beyond ~3000 events per CTA more CTAs make a
+        // slice slower (single DAVIS-240C slice: 0.247 ms at G = 16..32, 0.299 ms at G = 296; measured sweep
+        // in tools/sweep_single.py).
+        const long long per_slice = c->n_events / std::max(1, n_slices);
+        const int cap = (int)std::min<long long>(slots, std::max<long long>(16, per_slice / 3000));
+        g = std::max(std::min(g, cap), std::min(c->min_group, g));
+    }
     *G = g;
     *n_groups = std::min(groups, slots / g);
 }

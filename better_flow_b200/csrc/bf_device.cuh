@@ -686,32 +686,43 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
     const int warp = threadIdx.x >> 5;
     const bool one_chunk = n_cells <= BF_LIST_CAP;
     int n_live = -1;
+    // Live cells are dealt round-robin over the G * BF_NW warps of the group; on grids that need
+    // several list chunks the deal continues where the previous chunk stopped (restarting at warp 0
+    // for every chunk left the high ranks idle: 26 % of a 1280x720 iteration was barrier wait).
+    const int n_warps = G * BF_NW, my_warp = rank * BF_NW + warp;
+    int dealt = 0, dealt_clear = 0;
     for (int base = 0; base < n_cells; base += BF_LIST_CAP) {
         // (clearing first: it may borrow `list`, which must hold the CURRENT live cells when this returns)
         if (img_clear != nullptr && !(one_chunk && list_prev != nullptr)) {
             const int total = compact_cells(flags_clear, tag_clear, base, n_cells, list, scan);
-            for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+            int k0 = (my_warp - dealt_clear) % n_warps;
+            if (k0 < 0) k0 += n_warps;
+            for (int k = k0; k < total; k += n_warps) {
                 const int c = base + (int)list[k];
                 cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
             }
+            dealt_clear = (dealt_clear + total) % n_warps;
         }
         if (img != nullptr) {
             const int total = compact_cells(flags, tag, base, n_cells, list, scan);
             if (one_chunk) n_live = total;
+            int k0 = (my_warp - dealt) % n_warps;
+            if (k0 < 0) k0 += n_warps;
+            dealt = (dealt + total) % n_warps;
             if constexpr (MODE == 1) {
-                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                for (int k = k0; k < total; k += n_warps) {
                     const int c = base + (int)list[k];
                     const int ci = c / n_cj, cj = c - ci * n_cj;
                     local_cell_process<SH>(acc, img, pitch, pk, ci, cj, g.rows, g.cols);
                 }
             } else if (pk.fast) {
-                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                for (int k = k0; k < total; k += n_warps) {
                     const int c = base + (int)list[k];
                     const int ci = c / n_cj, cj = c - ci * n_cj;
                     cell_process<SH, MATERIALISE, true>(acc, img, pitch, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
                 }
             } else {
-                for (int k = rank * BF_NW + warp; k < total; k += G * BF_NW) {
+                for (int k = k0; k < total; k += n_warps) {
                     const int c = base + (int)list[k];
                     const int ci = c / n_cj, cj = c - ci * n_cj;
                     cell_process<SH, MATERIALISE, false>(acc, img, pitch, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
@@ -903,6 +914,33 @@ __device__ __forceinline__ void group_sums(BfSums &s, const double *partials, in
     s.cnt = v[0]; s.si = v[1]; s.sj = v[2]; s.sgx = v[3]; s.sgy = v[4];
     s.sigx = v[5]; s.sjgx = v[6]; s.sigy = v[7]; s.sjgy = v[8];
 }
+
+// The same sum for LARGE groups (a single slice on the whole GPU: G = 296), in two steps so that the
+// G records are fetched with one L2 round trip instead of G / 32 dependent ones (12 k of the 54 k
+// cycles of a DAVIS-240C single-slice iteration): every thread t < G takes record t, warps reduce,
+// warp 0 finishes from shared memory.  Fixed order => bit-identical in every CTA.  G <= BF_NT.
+__device__ __forceinline__ void group_sums_block_gather(const double *partials, int G, double *sred /* [BF_NW][BF_NSUMS] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v[BF_NSUMS];
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) v[k] = ((int)threadIdx.x < G) ? __ldcg(partials + threadIdx.x * BF_NSUMS + k) : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) sred[warp * BF_NSUMS + k] = v[k];
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void group_sums_block_finish(BfSums &s, const double *sred) {   // warp 0, after the gather
+    const int lane = threadIdx.x & 31;
+    double v[BF_NSUMS];
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) v[k] = warp_sum(lane < BF_NW ? sred[lane * BF_NSUMS + k] : 0.0);
+    s.cnt = v[0]; s.si = v[1]; s.sj = v[2]; s.sgx = v[3]; s.sgy = v[4];
+    s.sigx = v[5]; s.sjgx = v[6]; s.sigy = v[7]; s.sjgy = v[8];
+}
+#define BF_BLOCK_GATHER_MIN 48   // groups at least this large gather block-wide
 
 // sin/cos of the accumulated rotation.  |crl| is ~1e-4 rad in practice: a degree-11/10 Taylor
 // polynomial is accurate to < 1 ulp for |x| <= 2^-5 and costs ~20 dependent fp64 operations instead

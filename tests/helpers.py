@@ -53,3 +53,12 @@ def rel(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def same_model(a, b, rtol=1e-12):
+    """Two results of the same slice from launches with a different CTA grouping (batched vs alone, helped vs
+    not, another device count).  The integer image sums are order-independent, so occupancy counts must be
+    equal; the fp64 gradient moments are summed in a grouping-dependent order and may differ in the last bits."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return a[6] == b[6] and bool(np.allclose(a, b, rtol=rtol, atol=0))

@@ -6,6 +6,7 @@ import pytest
 
 import better_flow_b200 as bf
 from better_flow_b200 import synth
+from helpers import same_model
 
 pytestmark = pytest.mark.gpu
 
@@ -44,8 +45,8 @@ def test_config2_davis346_batch_of_64(oracle_port):
             alone = c.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=10)
             p = rng.permutation(len(s.fr_x))
             shuf = c.minimize(s.fr_x[p], s.fr_y[p], s.t_ns[p], scale=3, max_iter=10)
-            assert np.array_equal(alone["model"], res[k]["model"])
-            assert np.array_equal(shuf["model"], res[k]["model"])
+            assert np.array_equal(alone["model"], shuf["model"])      # same launch geometry: bit-identical
+            assert same_model(alone["model"], res[k]["model"])        # other grouping: fp64 moment sums to the last bits
     finally:
         c.close()
 

@@ -9,6 +9,7 @@ import pytest
 
 import better_flow_b200 as bf
 from better_flow_b200 import synth
+from helpers import same_model
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +34,7 @@ def same_results(a, b):
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert x["rc"] == y["rc"] and x["iters"] == y["iters"] and x["n_events"] == y["n_events"]
-        assert x["model"].tobytes() == y["model"].tobytes()
+        assert same_model(x["model"], y["model"])      # (another grouping of CTAs: fp64 moment sums to the last bits)
         assert x["dividers"].tobytes() == y["dividers"].tobytes()
 
 
