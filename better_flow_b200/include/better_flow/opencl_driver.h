@@ -8,6 +8,8 @@
 #ifndef BF_OPENCL_DRIVER_H
 #define BF_OPENCL_DRIVER_H
 
+#include <chrono>
+
 #include <better_flow/common.h>
 #include <bf_cuda.h>
 
@@ -39,6 +41,7 @@ public:
         const bool fits = s.ctx && s.rows == RES_X && s.cols == RES_Y && need_events <= s.events &&
                           need_slices <= s.slices && need_scale <= s.scale;
         if (!fits) {
+            const auto t0 = std::chrono::steady_clock::now();
             if (s.ctx) bf_ctx_destroy(s.ctx);
             s.rows = RES_X; s.cols = RES_Y;
             s.events = std::max<long long>(need_events + need_events / 4, 1 << 16);
@@ -49,6 +52,9 @@ public:
                 std::cerr << "bf_ctx_create failed: " << bf_last_error() << std::endl;
                 std::exit(1);
             }
+            if (std::getenv("BF_TIMING"))
+                std::cerr << "[timing] context (re)created for " << s.events << " events / " << s.slices << " slices in "
+                          << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;
         }
         return s.ctx;
     }

@@ -139,8 +139,16 @@ int main(int argc, char *argv[]) {
     if (gpus > 1 && batch < gpus) { fprintf(stderr, "--gpus=%d needs --batch of at least %d slices.\n", gpus, gpus); return 1; }
     (void)gpu; (void)img; (void)video;
 
+    const bool timing = std::getenv("BF_TIMING") != nullptr;
+    const auto wall_start = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (timing)
+            std::cerr << "[timing] " << what << " at " << std::chrono::duration<double>(std::chrono::steady_clock::now() - wall_start).count()
+                      << " s" << std::endl;
+    };
     bf::set_sensor(sensor_h, sensor_w);   // RES_X = rows, RES_Y = columns
     OpenCLDriver::init(device);           // same call site as the reference's -G branch (:132-133)
+    stamp("device selected");
 
     DVS_flow<EVENT_WIDTH, FROM_SEC(TIME_WIDTH)> estimator(event_refresh, FROM_SEC(time_refresh), 0, (size_t)max_events,
                                                           (sll)FROM_SEC(slice_time));
@@ -212,6 +220,7 @@ int main(int argc, char *argv[]) {
         std::cout << "Read and processed " << i << " events" << std::endl << std::flush;
     }
 
+    stamp("stream consumed");
     estimator.recompute();   // ensure that *every* event has been processed
     estimator.flush();
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
@@ -223,6 +232,8 @@ int main(int argc, char *argv[]) {
         LinearEventCloudTemplate<Event> accumulated = estimator.get_accumulated();
         EventFile::to_file_uv(&accumulated, outFileName);
     }
+    stamp("outputs written");
     CudaDriver::shutdown();
+    stamp("shutdown");
     return 0;
 }
