@@ -37,7 +37,9 @@
 #endif
 #define BF_BORDER 4            // zero border of the stored image (>= scale/2 + 1)
 #define BF_CELL_ROWS 8         // output rows per cell
-#define BF_LIST_CAP 4096       // active-cell list entries per scan chunk
+#ifndef BF_LIST_CAP
+#define BF_LIST_CAP 4096       // active-cell list entries per scan chunk (a multiple of BF_NT)
+#endif
 
 typedef unsigned long long u64;
 
