@@ -15,6 +15,15 @@ for G in (0, 8):
     ctx.run(True)
     print([r["iters"] for r in ctx.results()], ctx.get_option("group_size"))
     ctx.run_streamed(False); ctx.sync()
+# OptimizerLocal slices mixed with rolling ones, helpers joining from the first iterations (G = 2: 148 groups, 6 slices)
+ctx.set_option("group_size", 2)
+ctx.reset()
+for k, s in enumerate(sls):
+    if k % 2: ctx.add_local(s.fr_x, s.fr_y, s.t_ns, (1, 3)[k % 4 == 1])
+    else: ctx.add(s.fr_x, s.fr_y, s.t_ns, (1, 3, 5)[k % 3], 4)
+ctx.run(True)
+print([(r["rc"], r["iters"]) for r in ctx.results()])
+ctx.set_option("group_size", 0)
 s = sls[0]
 su_w, su_h = 3 * 179, 3 * 239
 img = ctx.time_img(s.fr_x.astype(float), s.fr_y.astype(float), s.t_ns, su_w, su_h, 3, 2, 2)
