@@ -112,7 +112,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
         if (leader && may_grow) {
             const unsigned st = ld_relaxed_u32(&ws->help_state);
             if (st == (unsigned)HELP_CLAIMED) ws->grow_iter = iter;
-            else if (st == (unsigned)HELP_JOINED && G + P.G <= BF_MAX_GROW * P.G) atomicExch(&ws->help_state, (unsigned)HELP_OPEN);
+            else if (st == (unsigned)HELP_JOINED && G + P.G <= P.max_grow * P.G) atomicExch(&ws->help_state, (unsigned)HELP_OPEN);
         }
         {
             const long long sp = group_barrier(&ws->bar, bar_target, G);   // B: all partial sums are visible
@@ -686,6 +686,7 @@ struct bf_ctx {
     int iter_cap = 20000;
     int min_events = 1000;
     int tail_help = 1;          // idle groups join slices that are still running when the queue is empty
+    int max_grow = 8;           // ... up to this many groups per slice
 
     // geometry of the stored images
     int pitch = 0, rows_alloc = 0;
@@ -946,6 +947,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
     else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
+    else if (!strcmp(key, "max_grow")) c->max_grow = (int)std::min<long long>(BF_MAX_GROW, std::max(1LL, value));
     else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
     else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = (value >= 4 && BF_NT <= 256) ? 4 : (value >= 2 ? 2 : 1);
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
@@ -1162,7 +1164,15 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     P.ready = ready;
     P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
     P.allow_help = (c->tail_help && c->n_groups > 1) ? 1 : 0;
-    P.part_stride = P.allow_help ? BF_MAX_GROW * c->G : c->G;
+    P.max_grow = std::max(1, std::min(c->max_grow, BF_MAX_GROW));
+    if (c->opt_group <= 0) {
+        // a slice stops profiting from more CTAs at ~800 events per CTA (but take at least 64): measured sweep,
+        // profiles/r1f_single_slice_sweep.txt
+        const long long per_slice = c->n_events / std::max(1, c->n_slices);
+        const long long want_ctas = std::max<long long>(64, per_slice / 800);
+        P.max_grow = (int)std::max<long long>(1, std::min<long long>(P.max_grow, (want_ctas + c->G - 1) / c->G));
+    }
+    P.part_stride = P.allow_help ? P.max_grow * c->G : c->G;
     P.join = c->d_join;
     P.groups_done = reinterpret_cast<unsigned *>(c->d_ctrl + 128);
     P.prof = nullptr;

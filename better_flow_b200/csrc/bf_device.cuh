@@ -96,7 +96,7 @@ struct GroupWs {
 // Helpers join one group at a time (the leader re-opens the slice once the previous helper is in), up
 // to BF_MAX_GROW groups per slice.  Only OptimizerRolling slices are helped.
 enum { HELP_CLOSED = 0, HELP_OPEN = 1, HELP_CLAIMED = 2, HELP_JOINED = 3 };
-#define BF_MAX_GROW 8          // a slice is worked on by at most this many groups
+#define BF_MAX_GROW 16         // capacity: a slice is worked on by at most this many groups (run-time limit: KParams::max_grow)
 
 struct JoinRecord {
     SliceDesc sd;
@@ -134,7 +134,8 @@ struct KParams {
     int want_events;
     int tab_rows, tab_cols;  // capacity of the per-slice cell tables in dynamic shared memory (max image rows / cols)
     int allow_help;          // tail helping enabled (needs BF_MAX_GROW x G partial-sum slots per group)
-    int part_stride;         // partial-sum records per group (G, or BF_MAX_GROW x G with helping)
+    int part_stride;         // partial-sum records per group (G, or max_grow x G with helping)
+    int max_grow;            // a slice is worked on by at most this many groups (<= BF_MAX_GROW)
     JoinRecord *join;        // [n_groups]
     unsigned *groups_done;   // groups that found the slice queue empty
     const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)

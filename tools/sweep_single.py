@@ -12,12 +12,12 @@ for name, cols, rows, rate, ss, mi in [("240C 10ms 30k", 240, 180, 3e6, 0.010, 1
     s = synth.cut_slices(st, ss)[0]
     ctx = bf.Context(rows, cols, 3, max_events=len(st) + 1024, max_slices=2, device=0)
     out = []
-    for G in (-1, 0, 16, 32, 64, 148, 296):
+    for G, mg in ((0, 8), (16, 4), (16, 6), (16, 8), (16, 12), (16, 16), (8, 16), (24, 8), (32, 4), (32, 8)):
         ctx.set_option("group_size", max(G, 0))
-        ctx.set_option("tail_help", 0 if G == -1 else 1)
+        ctx.set_option("max_grow", mg)
         ctx.reset(); ctx.add(s.fr_x, s.fr_y, s.t_ns, 3, mi); ctx.run()
         ms = min(ctx.time_launches(5) / 5 for _ in range(3))
         r = ctx.result(0)
-        out.append("%sG%dx%d %.3f" % ("nohelp " if G == -1 else "", ctx.get_option("group_size"), ctx.get_option("n_groups"), ms))
+        out.append("G%d^%d %.3f" % (ctx.get_option("group_size"), mg, ms))
     print("%-24s n %7d iters %3d : ms/launch  %s" % (name, len(s.fr_x), r["iters"], "  ".join(out)), flush=True)
     ctx.close()
