@@ -200,7 +200,8 @@ int main(int argc, char *argv[]) {
         std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;
     } else {
         std::cout << "Reading from file... (" << file << ")" << std::endl << std::flush;
-        TextEventReader event_file(file);   // block reader + from_chars, same values as `ifstream >>`
+        // block reader + from_chars (same values as `ifstream >>`), parsing one block ahead on a second thread
+        PrefetchingTextEventReader event_file(file);
         ull i = 0;
         double t = 0;
         uint x = 0, y = 0;

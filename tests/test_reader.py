@@ -21,10 +21,10 @@ def rd():
     inc = os.path.join(ROOT, "better_flow_b200", "include")
     hdrs = [os.path.join(inc, "better_flow", f) for f in os.listdir(os.path.join(inc, "better_flow"))]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + inc,
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-I" + inc,
                                "-I" + os.path.join(ROOT, "include"), src, "-o", so])
     lib = C.CDLL(so)
-    for f in (lib.rd_fast, lib.rd_iostream, lib.rd_from_file):
+    for f in (lib.rd_fast, lib.rd_iostream, lib.rd_from_file, lib.rd_prefetch):
         f.restype = C.c_longlong
     return lib
 
@@ -53,6 +53,8 @@ def test_reader_equals_iostream_on_a_synthetic_stream(rd, tmp_path):
     b = parse(rd, rd.rd_iostream, path, cap)
     assert a[0] == len(st)
     same(a, b)
+    same(parse(rd, rd.rd_prefetch, path, cap), b)            # background-thread variant: same records, same order
+    assert parse(rd, rd.rd_prefetch, path, 1000)[0] == 1000   # the consumer may stop early (the worker is joined cleanly)
     print("parse %d events: block reader %.3f s, iostream %.3f s (%.1fx)" % (a[0], a[5], b[5], b[5] / a[5]))
     assert a[5] < b[5]
 
@@ -79,6 +81,7 @@ def test_reader_edge_cases_equal_iostream(rd, tmp_path, text, expect):
     b = parse(rd, rd.rd_iostream, path, 16)
     assert b[0] == expect, "iostream baseline changed its mind"
     same(a, b)
+    same(parse(rd, rd.rd_prefetch, path, 16), b)
 
 
 def test_reader_long_lines_and_block_boundaries(rd, tmp_path):
