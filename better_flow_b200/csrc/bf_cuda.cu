@@ -66,7 +66,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
     // per-slice cell tables live behind the fixed part of the shared-memory block
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
-    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
+    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols, SH);
     __syncthreads();
 
     long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
@@ -233,7 +233,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
     double *partials = P.partials + (size_t)group * P.part_stride * BF_NSUMS;
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
-    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols);
+    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols, 2 * SH);
     if (threadIdx.x == 0) local_opt_init(S.lopt, S.g.scale);
     __syncthreads();
     int buf = 0;

@@ -294,18 +294,23 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
 // shared memory (the computed form is ~45 instructions per event, the table form ~12).
 //   row_tab[x] = (first flag index of x's cell row, +-n_cj or 0: offset to the neighbouring cell row to stamp too)
 //   col_tab[y] = (cell column of y, +-1 or 0)
+// `margin`: how far outside a cell's interior an event still matters to that cell's OUTPUT pixels.  An
+// output pixel only contributes when its own mean time is occupied, i.e. when an event lies within the
+// box radius SH of it -- so the neighbour cell is stamped for events within SH of the border, not within
+// the patch halo H = SH + 1 (the halo is what the cell READS, not what makes it live).  OptimizerLocal's
+// blur spreads one more box radius: margin 2 * SH.
 template <int SH>
-__device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab, int rows, int cols) {
+__device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab, int rows, int cols, int margin) {
     typedef CellCfg<SH> C;
     const int n_ci = (rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (cols + C::CW - 1) / C::CW;
     for (int x = threadIdx.x; x < rows; x += blockDim.x) {
         const int ci = x >> 3, lx = x & 7;
-        const int di = (lx < C::H && ci > 0) ? -n_cj : ((lx >= BF_CELL_ROWS - C::H && ci + 1 < n_ci) ? n_cj : 0);
+        const int di = (lx < margin && ci > 0) ? -n_cj : ((lx >= BF_CELL_ROWS - margin && ci + 1 < n_ci) ? n_cj : 0);
         row_tab[x] = make_int2(ci * n_cj, di);
     }
     for (int y = threadIdx.x; y < cols; y += blockDim.x) {
         const int cj = y / C::CW, ly = y - cj * C::CW;
-        const int dj = (ly < C::H && cj > 0) ? -1 : ((ly >= C::CW - C::H && cj + 1 < n_cj) ? 1 : 0);
+        const int dj = (ly < margin && cj > 0) ? -1 : ((ly >= C::CW - margin && cj + 1 < n_cj) ? 1 : 0);
         col_tab[y] = make_short2((short)cj, (short)dj);
     }
 }
