@@ -66,6 +66,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
     // per-slice cell tables live behind the fixed part of the shared-memory block
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
+    unsigned *bm = reinterpret_cast<unsigned *>(col_tab + P.tab_cols);   // stamp bitmap, all-zero between event passes
     fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols, SH);
     __syncthreads();
 
@@ -89,7 +90,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
         unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
         event_pass<SH>(P, S.sd, S.g, S.pk, S.proj, rank, G, iter == 0, iter > 0 || S.sd.has_init != 0, img_new, nullptr,
-                       flags_new, tag, row_tab, col_tab);
+                       flags_new, tag, row_tab, col_tab, bm);
         if (pf) __syncthreads();
         PF_MARK(PF_EVENT);
         {
@@ -233,6 +234,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
     double *partials = P.partials + (size_t)group * P.part_stride * BF_NSUMS;
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
+    unsigned *bm = reinterpret_cast<unsigned *>(col_tab + P.tab_cols);
     fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols, 2 * SH);
     if (threadIdx.x == 0) local_opt_init(S.lopt, S.g.scale);
     __syncthreads();
@@ -244,7 +246,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
         unsigned *flags_new = buf ? flags1 : flags0;
         unsigned *flags_old = buf ? flags0 : flags1;
         tag += 1;
-        local_event_pass<SH>(P, S.sd, S.g, S.pk, S.lopt.cur_nx, S.lopt.cur_ny, rank, P.G, img_new, flags_new, tag, row_tab, col_tab);
+        local_event_pass<SH>(P, S.sd, S.g, S.pk, S.lopt.cur_nx, S.lopt.cur_ny, rank, P.G, img_new, flags_new, tag, row_tab, col_tab, bm);
         group_barrier(&ws->bar, bar_target, P.G);
         Acc acc;
         acc_zero(acc);
@@ -366,6 +368,11 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
     long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
     const long long t_begin = pf ? clock64() : 0;
     fill_rcp_table(S.rcp_tab);   // made visible by the first group barrier's __syncthreads
+    if (P.bm_words > 0) {
+        unsigned *bm = reinterpret_cast<unsigned *>(smem_raw + sizeof(Smem) + (size_t)P.tab_rows * sizeof(int2) +
+                                                    (size_t)P.tab_cols * sizeof(short2));
+        for (int w = threadIdx.x; w < P.bm_words; w += BF_NT) bm[w] = 0u;
+    }
 
     for (;;) {
         const long long t_pro = pf ? clock64() : 0;
@@ -729,9 +736,12 @@ struct bf_ctx {
 };
 
 static size_t smem_bytes() { return sizeof(Smem); }
+// per-CTA stamp bitmap: one bit per cell flag (flag_elems is a multiple of 64)
+static int bm_words_of(const bf_ctx *c) { return BF_SMEM_STAMP ? (int)(c->flag_elems / 32) : 0; }
 // minimise kernel: fixed block + the per-slice cell tables (int2 per image row, short2 per image column)
 static size_t smem_bytes_min(const bf_ctx *c) {
-    return sizeof(Smem) + (size_t)c->max_scale * c->res_x * sizeof(int2) + (size_t)c->max_scale * c->res_y * sizeof(short2);
+    return sizeof(Smem) + (size_t)c->max_scale * c->res_x * sizeof(int2) + (size_t)c->max_scale * c->res_y * sizeof(short2) +
+           (size_t)bm_words_of(c) * sizeof(unsigned);
 }
 
 static int ensure_device() {
@@ -962,6 +972,7 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!strcmp(key, "image_budget_mb")) return c->image_budget_mb;
     if (!strcmp(key, "iter_cap")) return c->iter_cap;
     if (!strcmp(key, "tail_help")) return c->tail_help;
+    if (!strcmp(key, "smem_stamp")) return BF_SMEM_STAMP;
     if (!strcmp(key, "min_events")) return c->min_events;
     if (!strcmp(key, "sms")) return c->sms;
     if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;
@@ -1163,6 +1174,7 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
     P.ready = ready;
     P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
+    P.bm_words = bm_words_of(c);
     P.allow_help = (c->tail_help && c->n_groups > 1) ? 1 : 0;
     P.max_grow = std::max(1, std::min(c->max_grow, BF_MAX_GROW));
     if (c->opt_group <= 0) {

@@ -29,6 +29,9 @@
 
 // ---- compile-time geometry -------------------------------------------------------------------
 #ifndef BF_NT
+#ifndef BF_SMEM_STAMP
+#define BF_SMEM_STAMP 1        // live cells are stamped in a per-CTA shared-memory bitmap, flushed once per event pass
+#endif
 #define BF_NT 512              // threads per CTA (16 warps)
 #endif
 #define BF_NW (BF_NT / 32)
@@ -133,6 +136,7 @@ struct KParams {
     int iter_cap;
     int want_events;
     int tab_rows, tab_cols;  // capacity of the per-slice cell tables in dynamic shared memory (max image rows / cols)
+    int bm_words;            // words of the per-CTA stamp bitmap behind the cell tables (0: stamp the global flags directly)
     int allow_help;          // tail helping enabled (needs BF_MAX_GROW x G partial-sum slots per group)
     int part_stride;         // partial-sum records per group (G, or max_grow x G with helping)
     int max_grow;            // a slice is worked on by at most this many groups (<= BF_MAX_GROW)
@@ -328,6 +332,42 @@ __device__ __forceinline__ void mark_cells_tab(unsigned *flags, unsigned tag, in
     }
 }
 
+// The same stamping into a per-CTA bitmap in shared memory (one bit per cell) instead of the global flag array:
+// a slice's events stamp each live cell ~50 times per iteration, and every stamp used to be a 4-byte global
+// store on its own L2 sector (more L2 write transactions than the splat itself).  The CTA sets bits while it
+// walks its events and writes the tag once per live cell afterwards (flush_stamp_bitmap).
+__device__ __forceinline__ void stamp_bit(unsigned *bm, int f) {
+    const unsigned b = 1u << (f & 31);
+    if (!(bm[f >> 5] & b)) atomicOr(bm + (f >> 5), b);
+}
+__device__ __forceinline__ void mark_cells_bm(unsigned *bm, int x, int y, const int2 *row_tab, const short2 *col_tab) {
+    const int2 r = row_tab[x];
+    const short2 c = col_tab[y];
+    const int f = r.x + (int)c.x;
+    const int dj = (int)c.y;
+    stamp_bit(bm, f);
+    if (dj != 0) stamp_bit(bm, f + dj);
+    if (r.y != 0) {
+        stamp_bit(bm, f + r.y);
+        if (dj != 0) stamp_bit(bm, f + r.y + dj);
+    }
+}
+// CTA-wide: write `tag` to the flag of every cell whose bit is set and leave the bitmap all-zero again.
+__device__ __forceinline__ void flush_stamp_bitmap(unsigned *bm, unsigned *flags, unsigned tag, int n_cells) {
+    __syncthreads();
+    const int words = (n_cells + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        unsigned m = bm[w];
+        if (m == 0u) continue;
+        bm[w] = 0u;
+        do {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1u;
+            flags[w * 32 + b] = tag;
+        } while (m != 0u);
+    }
+}
+
 // ---- event pass: clear old pixel, re-project, splat --------------------------------------------
 // One thread per event, CTA `rank` of the group owns a contiguous chunk (same chunk every
 // iteration, so each thread re-reads the state it wrote itself).
@@ -349,6 +389,7 @@ struct EventCtx {
     unsigned tag;
     const int2 *row_tab;
     const short2 *col_tab;
+    unsigned *bm;            // per-CTA stamp bitmap in shared memory, or null: stamp the global flags directly
 };
 
 // `st` carries the event's state in and, when the event is (re-)projected, its new state out.
@@ -375,14 +416,19 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 &st
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
         red_add_u64(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
+#if BF_SMEM_STAMP
+        mark_cells_bm(c.bm, x, y, c.row_tab, c.col_tab);
+#else
         mark_cells_tab(c.flags, c.tag, x, y, c.row_tab, c.col_tab);
+#endif
     }
 }
 
 template <int SH>
 __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, int G, bool first, bool project, u64 *img_new,
-                           double2 *out_nxy, unsigned *flags, unsigned tag, const int2 *row_tab, const short2 *col_tab) {
+                           double2 *out_nxy, unsigned *flags, unsigned tag, const int2 *row_tab, const short2 *col_tab,
+                           unsigned *bm = nullptr) {
     typedef CellCfg<SH> C;
     const int per = (((sd.n + G - 1) / G) + 31) & ~31;
     const int lo = rank * per;
@@ -396,7 +442,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     c.n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS;
     c.n_cj = (g.cols + C::CW - 1) / C::CW;
     c.first = first; c.project = project; c.img_new = img_new; c.flags = flags; c.tag = tag;
-    c.row_tab = row_tab; c.col_tab = col_tab;
+    c.row_tab = row_tab; c.col_tab = col_tab; c.bm = bm;
     // Events are taken in PAIRS aligned in the batch arrays (one 16-byte load brings two events, one
     // more their two states, one 16-byte store writes the states back); a pair that straddles the
     // chunk boundary has its foreign half predicated off.  Software pipeline: the loads of trip
@@ -441,6 +487,9 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         }
         e = ne; st = nst;
     }
+#if BF_SMEM_STAMP
+    if (img_new != nullptr) flush_stamp_bitmap(bm, flags, tag, c.n_ci * c.n_cj);   // (cnt is CTA-uniform: every thread gets here)
+#endif
 }
 
 // ---- fast unpack of a packed box sum ---------------------------------------------------------------
@@ -862,7 +911,7 @@ __device__ __forceinline__ bool local_opt_advance(LocalOpt &o, double cnt, doubl
 template <int SH>
 __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk, double nx,
                                  double ny, int rank, int G, u64 *img_new, unsigned *flags, unsigned tag, const int2 *row_tab,
-                                 const short2 *col_tab) {
+                                 const short2 *col_tab, unsigned *bm = nullptr) {
     const int per = (((sd.n + G - 1) / G) + 31) & ~31;
     const int lo = rank * per;
     const int cnt = min(sd.n, lo + per) - lo;
@@ -890,9 +939,19 @@ __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const Bf
             const int xc = x + g.half, yc = y + g.half;                           // :136-137
             const u64 dt = (u64)((long long)t - (long long)pk.t_min);
             red_add_u64(img_new + pixel_offset(xc, yc, P.pitch), one + (dt >> pk.q));
+#if BF_SMEM_STAMP
+            mark_cells_bm(bm, xc, yc, row_tab, col_tab);
+#else
             mark_cells_tab(flags, tag, xc, yc, row_tab, col_tab);
+#endif
         }
     }
+#if BF_SMEM_STAMP
+    {
+        typedef CellCfg<SH> C;
+        flush_stamp_bitmap(bm, flags, tag, ((g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS) * ((g.cols + C::CW - 1) / C::CW));
+    }
+#endif
 }
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):
