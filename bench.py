@@ -37,16 +37,32 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-SENSOR_COLS, SENSOR_ROWS = 240, 180
-RATE_EPS = 3e6
-SLICE_S = 0.030
+# BASELINE.json configurations that fit one GPU.  The default, cfg2, is the one the metric is
+# quoted on (configs[1]); the others are selectable with --config for the multi-GPU runs BASELINE.json names
+# (cfg4: slice-sharded over 2/4/8 GPUs, cfg5: 8 GPUs + one NCCL gather) -- same step, same JSON line.
+#   cols, rows, events/s, slice length, slices per step per GPU, max_iter, label
+CONFIGS = {
+    # 4 slices per CTA group (148 groups of 2); 592 x ~90 k events x 8 B = 426 MB of events > 126 MB L2
+    "cfg2": (240, 180, 3e6, 0.030, 592, -1, "DAVIS-240C 240x180 synthetic 3 Mev/s contour stream, 30 ms slices (~90k events)"),
+    "cfg3": (346, 260, 2e6, 0.050, 64, -1, "DAVIS-346 346x260 synthetic 2 Mev/s contour stream, 50 ms slices (~100k events), 64 slices batched per launch"),
+    "cfg4": (640, 480, 10e6, 0.020, 128, -1, "640x480 synthetic 10 Mev/s contour stream, 20 ms slices (200k events)"),
+    "cfg5": (1280, 720, 100e6, 0.010, 32, -1, "1280x720 synthetic 100 Mev/s contour stream, 10 ms slices (1M events)"),
+}
 SCALE = 3
-MAX_ITER = -1
-SLICES_PER_STEP = 592          # 4 slices per CTA group (148 groups of 2); 592 x ~90 k events x 8 B = 426 MB of events > 126 MB L2
 METRIC = "Mevents/sec motion-compensated"
 UNIT = "Mevents/s"
-WORKLOAD = ("DAVIS-240C 240x180 synthetic 3 Mev/s contour stream, 30 ms slices (~90k events), "
-            "GD to convergence, scale 3, stm-disabled, %d slices per step" % SLICES_PER_STEP)
+
+
+def select_config(name, slices=None):
+    global SENSOR_COLS, SENSOR_ROWS, RATE_EPS, SLICE_S, SLICES_PER_STEP, MAX_ITER, WORKLOAD, CONFIG_NAME
+    SENSOR_COLS, SENSOR_ROWS, RATE_EPS, SLICE_S, SLICES_PER_STEP, MAX_ITER, label = CONFIGS[name]
+    if slices:
+        SLICES_PER_STEP = slices
+    CONFIG_NAME = name
+    WORKLOAD = "%s, GD to convergence, scale 3, stm-disabled, %d slices per step" % (label, SLICES_PER_STEP)
+
+
+select_config("cfg2")
 
 
 def measured_peak_gbs():
@@ -132,11 +148,26 @@ def cpu_reference_run(slices, max_seconds=None):
             "kind": "reference" if use_ref else "port", "cores": cores}
 
 
+def one_core_baseline(n_slices):
+    """The same CPU path pinned to ONE core (SURVEY 8d asks for both figures): a child process, because the
+    thread count of the compiled reference is fixed at its first parallel_for."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--config", CONFIG_NAME, "--cpu-one-core", str(n_slices)]
+    try:
+        if subprocess.run(["taskset", "-c", "0", "true"], capture_output=True).returncode == 0:
+            cmd = ["taskset", "-c", "0"] + cmd
+        env = dict(os.environ, BF_ORACLE_THREADS="1", OMP_NUM_THREADS="1")
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        r = json.loads(out)
+        return r["events"] / r["seconds"] / 1e6
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    per_step = 6
+    per_step = {"cfg2": 6, "cfg3": 4, "cfg4": 2, "cfg5": 1}[CONFIG_NAME]   # ~0.2-3 s of CPU work per slice
     slices = make_batch(1000, per_step * (args.steps + args.warmup))
     k = 0
     for _ in range(args.warmup):
@@ -167,17 +198,25 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slices", type=int, default=SLICES_PER_STEP)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the one the metric is quoted on)")
+    ap.add_argument("--slices", type=int, default=0, help="slices per step per GPU (0 = the configuration's)")
     ap.add_argument("--group-size", type=int, default=0)
     ap.add_argument("--upload-chunks", type=int, default=0, help="chunks of the streamed event upload (0 = library default)")
     ap.add_argument("--cpu-sample", type=int, default=24, help="slices timed on the CPU baseline (0 = skip)")
+    ap.add_argument("--cpu-one-core", type=int, default=0, help=argparse.SUPPRESS)   # child mode of one_core_baseline()
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    select_config(args.config, args.slices)
+    args.slices = SLICES_PER_STEP
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.cpu_one_core > 0:
+        info = cpu_reference_run(make_batch(100, args.cpu_one_core))
+        print(json.dumps({"events": info["events"], "seconds": info["seconds"], "cores": info["cores"], "iters_mean": info["iters_mean"]}))
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -308,13 +347,17 @@ def main():
         if args.cpu_sample > 0 and world == 1:
             info = cpu_reference_run(slices[:args.cpu_sample], max_seconds=40.0)
             cpu = {"value": info["events"] / info["seconds"] / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                   "value_1core": one_core_baseline({"cfg2": 12, "cfg3": 8, "cfg4": 3, "cfg5": 1}[CONFIG_NAME]),
                    "sample": "first %d slices of the same batch, OptimizerRolling::run() wall time only, iters mean %.1f"
                              % (info["slices"], info["iters_mean"])}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (%.0f MB of events per GPU per step)" % (n_events * 8 / 1e6),
+            "config": {"workload": WORKLOAD, "name": CONFIG_NAME,
+                       "l2": ("inputs larger than L2 (%.0f MB of events per GPU per step)" % (n_events * 8 / 1e6)) if n_events * 8 > 130e6
+                             else ("working set larger than L2 (%.0f MB of events + as much state + %.0f MB of slice images in flight per GPU)"
+                                   % (n_events * 8 / 1e6, 16.0 * P * ctx.get_option("n_groups") / 1e6)),
                        "events_per_step_per_gpu": n_events, "pixels_per_image": P, "iters_mean": float(np.mean(iters)),
                        "iters_max": int(max(iters)), "all_converged": bool(ok), "group_size": ctx.get_option("group_size"),
                        "n_groups": ctx.get_option("n_groups"),
