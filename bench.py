@@ -148,6 +148,28 @@ def cpu_reference_run(slices, max_seconds=None):
             "kind": "reference" if use_ref else "port", "cores": cores}
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """N > 1: run this rank (and so allocate its pinned staging buffer, first touch) on the CPUs of the NUMA node
+    its GPU hangs off; 8 ranks streaming 426 MB per step each otherwise cross the socket link.  Best effort."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def one_core_baseline(n_slices):
     """The same CPU path pinned to ONE core (SURVEY 8d asks for both figures): a child process, because the
     thread count of the compiled reference is fixed at its first parallel_for."""
@@ -189,10 +211,30 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """Everything any library prints to stdout from here on (NCCL's version banner, ...) goes to stderr; the one
+    JSON line is written to the original stdout by emit()."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -215,7 +257,7 @@ def main():
 
     if args.cpu_one_core > 0:
         info = cpu_reference_run(make_batch(100, args.cpu_one_core))
-        print(json.dumps({"events": info["events"], "seconds": info["seconds"], "cores": info["cores"], "iters_mean": info["iters_mean"]}))
+        emit({"events": info["events"], "seconds": info["seconds"], "cores": info["cores"], "iters_mean": info["iters_mean"]})
         return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -227,6 +269,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -257,9 +301,14 @@ def main():
     h2d = n_events * 8 + len(slices) * 120   # 8-byte event records + the slice table
     d2h = len(slices) * bf.RESULT_BYTES
 
-    gather_buf = None
+    # N > 1: the per-slice flow records of a step are gathered with ONE NCCL all_gather per step.  It runs on a
+    # side stream behind a device-side snapshot of the records, so the exchange of step k overlaps the
+    # minimisation of step k + 1 instead of making all ranks wait for the slowest one at every step.
+    gather_buf = gather_src = side = None
     if dist is not None:
         gather_buf = torch.empty(world * len(slices) * bf.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+        gather_src = torch.empty(len(slices) * bf.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+        side = torch.cuda.Stream()
 
     class _Dev:  # __cuda_array_interface__ view of the device result records
         def __init__(self, ptr, nbytes):
@@ -270,7 +319,13 @@ def main():
             return
         ptr, nbytes = ctx.results_device()
         mine = torch.as_tensor(_Dev(ptr, nbytes), device="cuda")
-        dist.all_gather_into_tensor(gather_buf, mine)
+        side.wait_stream(stream)                      # the launch that produced the records
+        with torch.cuda.stream(side):
+            gather_src[:nbytes].copy_(mine, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+            dist.all_gather_into_tensor(gather_buf, gather_src)
+        stream.wait_event(copied)                     # the next launch overwrites the records
 
     def step_resident():
         ctx.launch(False)
@@ -291,6 +346,8 @@ def main():
             e0.record(stream)
             for _ in range(k):
                 fn()
+            if side is not None:
+                stream.wait_stream(side)              # the last gather belongs to the timed region
             e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -374,7 +431,7 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
