@@ -737,7 +737,7 @@ struct bf_ctx {
 
 static size_t smem_bytes() { return sizeof(Smem); }
 // per-CTA stamp bitmap: one bit per cell flag (flag_elems is a multiple of 64)
-static int bm_words_of(const bf_ctx *c) { return BF_SMEM_STAMP ? (int)(c->flag_elems / 32) : 0; }
+static int bm_words_of(const bf_ctx *c) { return (int)(c->flag_elems / 32); }
 // minimise kernel: fixed block + the per-slice cell tables (int2 per image row, short2 per image column)
 static size_t smem_bytes_min(const bf_ctx *c) {
     return sizeof(Smem) + (size_t)c->max_scale * c->res_x * sizeof(int2) + (size_t)c->max_scale * c->res_y * sizeof(short2) +
@@ -972,7 +972,6 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!strcmp(key, "image_budget_mb")) return c->image_budget_mb;
     if (!strcmp(key, "iter_cap")) return c->iter_cap;
     if (!strcmp(key, "tail_help")) return c->tail_help;
-    if (!strcmp(key, "smem_stamp")) return BF_SMEM_STAMP;
     if (!strcmp(key, "min_events")) return c->min_events;
     if (!strcmp(key, "sms")) return c->sms;
     if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;

@@ -29,9 +29,6 @@
 
 // ---- compile-time geometry -------------------------------------------------------------------
 #ifndef BF_NT
-#ifndef BF_SMEM_STAMP
-#define BF_SMEM_STAMP 1        // live cells are stamped in a per-CTA shared-memory bitmap, flushed once per event pass
-#endif
 #define BF_NT 512              // threads per CTA (16 warps)
 #endif
 #define BF_NW (BF_NT / 32)
@@ -342,21 +339,7 @@ __device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab,
         col_tab[y] = make_short2((short)cj, (short)dj);
     }
 }
-__device__ __forceinline__ void mark_cells_tab(unsigned *flags, unsigned tag, int x, int y, const int2 *row_tab,
-                                               const short2 *col_tab) {
-    const int2 r = row_tab[x];
-    const short2 c = col_tab[y];
-    const int f = r.x + (int)c.x;
-    const int dj = (int)c.y;
-    flags[f] = tag;
-    if (dj != 0) flags[f + dj] = tag;
-    if (r.y != 0) {
-        flags[f + r.y] = tag;
-        if (dj != 0) flags[f + r.y + dj] = tag;
-    }
-}
-
-// The same stamping into a per-CTA bitmap in shared memory (one bit per cell) instead of the global flag array:
+// In the minimise kernel the stamps go to a per-CTA bitmap in shared memory (one bit per cell) instead of the global flag array:
 // a slice's events stamp each live cell ~50 times per iteration, and every stamp used to be a 4-byte global
 // store on its own L2 sector (more L2 write transactions than the splat itself).  The CTA sets bits while it
 // walks its events and writes the tag once per live cell afterwards (flush_stamp_bitmap).
@@ -413,7 +396,7 @@ struct EventCtx {
     unsigned tag;
     const int2 *row_tab;
     const short2 *col_tab;
-    unsigned *bm;            // per-CTA stamp bitmap in shared memory, or null: stamp the global flags directly
+    unsigned *bm;            // per-CTA stamp bitmap in shared memory (one bit per cell)
 };
 
 // `st` carries the event's state in and, when the event is (re-)projected, its new state out.
@@ -440,11 +423,7 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 &st
     if (c.img_new != nullptr && !noise && event_pixel(prx, pry, c.pm, x, y)) {
         const u64 dt = (u64)((long long)t - (long long)c.t_min);
         red_add_u64(c.img_new + pixel_offset(x, y, c.pm.pitch), c.one + (dt >> c.tq));
-#if BF_SMEM_STAMP
         mark_cells_bm(c.bm, x, y, c.row_tab, c.col_tab);
-#else
-        mark_cells_tab(c.flags, c.tag, x, y, c.row_tab, c.col_tab);
-#endif
     }
 }
 
@@ -480,11 +459,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
     float4 st = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (p < p1) {
         e = ld_nc_u32x4(ev4 + p);
-#ifdef BF_STATE_CG
-        if (!first) st = __ldcg(st4 + p);
-#else
         if (!first) st = ld_state4(st4 + p);   // (when a group grows -- helping -- its members invalidate L1 first, see slice_loop)
-#endif
     }
     for (; p < p1; p += BF_NT) {
         const long long np = p + BF_NT;
@@ -492,11 +467,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         float4 nst = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (np < p1) {
             ne = ld_nc_u32x4(ev4 + np);
-#ifdef BF_STATE_CG
-            if (!first) nst = __ldcg(st4 + np);
-#else
             if (!first) nst = ld_state4(st4 + np);
-#endif
         }
         const long long i0 = 2 * p, i1 = i0 + 1;
         const bool v0 = i0 >= gs, v1 = i1 < ge;                  // (i0 < ge and i1 >= gs hold by construction)
@@ -511,9 +482,7 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
         }
         e = ne; st = nst;
     }
-#if BF_SMEM_STAMP
     if (img_new != nullptr) flush_stamp_bitmap(bm, flags, tag, c.n_ci * c.n_cj);   // (cnt is CTA-uniform: every thread gets here)
-#endif
 }
 
 // ---- fast unpack of a packed box sum ---------------------------------------------------------------
@@ -963,19 +932,13 @@ __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const Bf
             const int xc = x + g.half, yc = y + g.half;                           // :136-137
             const u64 dt = (u64)((long long)t - (long long)pk.t_min);
             red_add_u64(img_new + pixel_offset(xc, yc, P.pitch), one + (dt >> pk.q));
-#if BF_SMEM_STAMP
             mark_cells_bm(bm, xc, yc, row_tab, col_tab);
-#else
-            mark_cells_tab(flags, tag, xc, yc, row_tab, col_tab);
-#endif
         }
     }
-#if BF_SMEM_STAMP
     {
         typedef CellCfg<SH> C;
         flush_stamp_bitmap(bm, flags, tag, ((g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS) * ((g.cols + C::CW - 1) / C::CW));
     }
-#endif
 }
 
 // Sum the G per-CTA partial records of a group in a fixed order (lane-strided, then butterfly):
