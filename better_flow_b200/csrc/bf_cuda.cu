@@ -1077,6 +1077,7 @@ int bf_local_minimize(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, con
 int bf_batch_add_packed(bf_ctx *c, const bf_event *events, int n, int scale, int max_iter, const bf_model *init) {
     if (!c || n < 0 || (n > 0 && !events)) return fail(BF_ERR_ARG, "bf_batch_add_packed: bad arguments");
     if (c->n_events + n > c->max_events) return fail(BF_ERR_ARG, "batch event capacity exceeded (%lld)", c->max_events);
+    if (!bf_events_in_sensor(events, n, c->res_x, c->res_y)) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
     memcpy(c->h_events + c->n_events, events, (size_t)n * sizeof(bf_event));
     const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
     if (slot >= 0) c->n_events += n;
@@ -1091,6 +1092,7 @@ bf_event *bf_batch_staging(bf_ctx *c, long long *capacity) {
 
 int bf_batch_add_staged(bf_ctx *c, long long offset, int n, int scale, int max_iter, const bf_model *init) {
     if (!c || n < 0 || offset < 0 || offset + n > c->max_events) return fail(BF_ERR_ARG, "bf_batch_add_staged: bad range");
+    if (!bf_events_in_sensor(c->h_events + offset, n, c->res_x, c->res_y)) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
     const int slot = add_desc(c, offset, n, scale, max_iter, init);
     if (slot >= 0) c->n_events = std::max(c->n_events, offset + n);
     return slot;

@@ -60,6 +60,16 @@ struct BfPack {
     unsigned long long sum_mask;
 };
 
+// Every event of a compact batch inside the res_x x res_y sensor?  (Host-side precondition check of
+// bf_batch_add_packed / bf_batch_add_staged: the device sizes a slice's images from the bounding box of its
+// events, so a coordinate beyond the context's sensor would index past the image allocation.)
+BF_HD bool bf_events_in_sensor(const bf_event *ev, long long n, int res_x, int res_y) {
+    unsigned bad = 0;
+    for (long long i = 0; i < n; ++i)
+        bad |= (unsigned)((int)ev[i].fr_x >= res_x) | (unsigned)((int)(ev[i].fr_y & 0x7fffu) >= res_y);
+    return bad == 0;
+}
+
 BF_HD int bf_bits(unsigned long long v) {
     int b = 0;
     while (v) { ++b; v >>= 1; }

@@ -120,14 +120,16 @@ int bf_batch_reset(bf_ctx *ctx);
  * Returns the slot index (>= 0) of the slice inside the batch. */
 int bf_batch_add(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns,
                  const uint8_t *noise, int n, int scale, int max_iter, const bf_model *init);
-/* Same, events already in the compact 8-byte layout (no host-side packing pass). */
+/* Same, events already in the compact 8-byte layout (no host-side packing pass).  Like bf_batch_add, refuses
+ * (BF_ERR_ARG) a batch holding a coordinate outside the context's sensor: the device sizes a slice's images
+ * from the bounding box of its events. */
 int bf_batch_add_packed(bf_ctx *ctx, const bf_event *events, int n, int scale, int max_iter,
                         const bf_model *init);
 
 /* Pinned host staging area the batch is assembled in (so callers can fill it in place):
  * returns the base of the event staging buffer; *capacity = max_events. */
 bf_event *bf_batch_staging(bf_ctx *ctx, long long *capacity);
-/* Declare a slice that already lives in the staging buffer at [offset, offset+n). */
+/* Declare a slice that already lives in the staging buffer at [offset, offset+n) (same coordinate check). */
 int bf_batch_add_staged(bf_ctx *ctx, long long offset, int n, int scale, int max_iter,
                         const bf_model *init);
 

@@ -39,6 +39,11 @@ float lg_accumulate(int n_total, int t_min, int t_max, int k, const int *t) {
     return bf_unpack_avg(p, acc);
 }
 
+// Precondition check of the packed / staged batch entry points (8-byte records: u16 fr_x, u16 fr_y | noise bit, i32 t).
+int lg_events_in_sensor(const void *events, long long n, int res_x, int res_y) {
+    return bf_events_in_sensor(static_cast<const bf_event *>(events), n, res_x, res_y) ? 1 : 0;
+}
+
 // Replay of OptimizerRolling::run's control flow on a recorded sequence of per-iteration sums.
 // sums: steps x 9 doubles.  Returns the number of steps consumed; out: model(11) + dividers(4) + rc.
 int lg_replay(int steps, const double *sums, int x_min, int x_max, int y_min, int y_max, int scale, int i0, int j0,

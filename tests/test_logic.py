@@ -148,3 +148,37 @@ def test_gd_control_flow_replay_matches_oracle(lg, oracle_port):
     assert np.array_equal(out[11:15].astype(np.float32), want["dividers"])
     assert np.allclose(out[7:11], want["model"][7:11], rtol=1e-9, atol=0)
     assert out[6] == want["model"][6]
+
+
+def test_packed_events_are_checked_against_the_sensor(lg):
+    """bf_batch_add_packed / bf_batch_add_staged refuse coordinates beyond the context's sensor (the device
+    sizes the images from the events' bounding box); the noise bit of fr_y is not a coordinate bit."""
+    import better_flow_b200 as bf
+    rng = np.random.default_rng(3)
+    n = 4097
+    fx = rng.integers(0, 180, n).astype(np.uint16)
+    fy = rng.integers(0, 240, n).astype(np.uint16)
+    t = rng.integers(0, 30_000_000, n).astype(np.int32)
+    noise = (rng.random(n) < 0.1).astype(np.uint8)
+    ev = np.ascontiguousarray(bf.pack_events(fx, fy, t, noise))
+    assert ev.dtype.itemsize == 8
+
+    def ok(a, rx=180, ry=240):
+        return lg.lg_events_in_sensor(a.ctypes.data_as(C.c_void_p), C.c_longlong(len(a)), rx, ry)
+
+    assert ok(ev) == 1
+    assert ok(ev[:0]) == 1
+    assert ok(ev, 179, 240) == (1 if fx.max() < 179 else 0)
+    for pos in (0, n // 2, n - 1):
+        bad = ev.copy()
+        raw = bad.view(np.uint16).reshape(-1, 4)
+        raw[pos, 0] = 180                       # fr_x == res_x
+        assert ok(bad) == 0
+        bad = ev.copy()
+        raw = bad.view(np.uint16).reshape(-1, 4)
+        raw[pos, 1] = 240 | 0x8000              # fr_y == res_y, noise bit set
+        assert ok(bad) == 0
+        bad = ev.copy()
+        raw = bad.view(np.uint16).reshape(-1, 4)
+        raw[pos, 1] = 239 | 0x8000              # in range + noise bit: fine
+        assert ok(bad) == 1
