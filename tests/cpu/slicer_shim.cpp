@@ -70,3 +70,38 @@ extern "C" int sl_stream(int config, int n, const uint32_t *fr_x, const uint32_t
     }
     return -1;
 }
+
+// ---- the per-event formulas of the host mirror (better_flow/event.h), for comparison with the oracle ----
+// Event::project_4param_reinit + apply_project (event.h:99-110,164-168), restarted from the given pr.
+extern "C" void ev_project_4param(int n, const uint32_t *fr_x, const uint32_t *fr_y, const long long *t_local, double *pr_x,
+                                  double *pr_y, double *nx, double *ny, double dnx, double dny, double cx, double cy,
+                                  double div, double crl) {
+    for (int i = 0; i < n; ++i) {
+        Event e(fr_x[i], fr_y[i], 0);
+        e.t = t_local[i];
+        e.pr_x = pr_x[i]; e.pr_y = pr_y[i];
+        e.project_4param_reinit(dnx, dny, cx, cy, div, crl);
+        pr_x[i] = e.pr_x; pr_y[i] = e.pr_y; nx[i] = e.nx; ny[i] = e.ny;
+    }
+}
+
+// Event::compute_uv (event.h:135-142)
+extern "C" void ev_compute_uv(int n, const double *nx, const double *ny, double *u, double *v) {
+    for (int i = 0; i < n; ++i) {
+        Event e(0, 0, 0);
+        e.nx = nx[i]; e.ny = ny[i];
+        e.compute_uv();
+        u[i] = e.u; v[i] = e.v;
+    }
+}
+
+// Event::set_local_time (event.h:61-63) and Event::project (event.h:144-149 via apply_project)
+extern "C" void ev_project(int n, const uint32_t *fr_x, const uint32_t *fr_y, const unsigned long long *ts,
+                           unsigned long long t0, double nx, double ny, long long *t_local, double *pr_x, double *pr_y) {
+    for (int i = 0; i < n; ++i) {
+        Event e(fr_x[i], fr_y[i], ts[i]);
+        e.set_local_time(t0);
+        e.project(nx, ny);
+        t_local[i] = e.t; pr_x[i] = e.pr_x; pr_y[i] = e.pr_y;
+    }
+}

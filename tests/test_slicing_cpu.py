@@ -113,3 +113,43 @@ def test_run_time_sized_buffer_equals_template_sized(sl):
     assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist()
     c = slices_of(sl, st.y, st.x, st.t_ns, config=2, capacity=10000, span_ns=30_000_000)
     assert max(int(i[1]) for i in c[0]) <= 10000 and max(int(i[2]) for i in c[0]) <= 30_000_000
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def test_host_event_formulas_match_the_oracle(sl, oracle_port):
+    """The per-event formulas the host mirror keeps (better_flow/event.h: set_local_time, project,
+    project_4param_reinit, compute_uv -- used for set-up, -o output and OptimizerLocal's write-back) against the
+    oracle restatement (itself pinned bit-for-bit on the compiled reference), to the last bit."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    fx = rng.integers(0, 180, n).astype(np.uint32)
+    fy = rng.integers(0, 240, n).astype(np.uint32)
+    t = rng.integers(-2_000_000, 200_000_000, n).astype(np.int64)       # local times may be negative (dvs_flow.h:187-190)
+    pr_x = fx + rng.normal(0, 2.0, n)
+    pr_y = fy + rng.normal(0, 2.0, n)
+    args = (0.031, -0.052, 88.5, 121.25, 3.5e-4, -2.25e-3)
+    want = oracle_port.project(fx, fy, t, pr_x, pr_y, *args)
+    px, py = pr_x.copy(), pr_y.copy()
+    nx, ny = np.zeros(n), np.zeros(n)
+    sl.ev_project_4param(n, _p(fx, C.c_uint32), _p(fy, C.c_uint32), _p(t, C.c_longlong), _p(px, C.c_double), _p(py, C.c_double),
+                         _p(nx, C.c_double), _p(ny, C.c_double), *[C.c_double(a) for a in args])
+    for got, w in zip((px, py, nx, ny), want):
+        assert np.array_equal(got, w)
+
+    u, v = np.zeros(n), np.zeros(n)
+    sl.ev_compute_uv(n, _p(nx, C.c_double), _p(ny, C.c_double), _p(u, C.c_double), _p(v, C.c_double))
+    wu, wv = oracle_port.compute_uv(nx, ny)
+    assert np.array_equal(u, wu) and np.array_equal(v, wv)
+
+    # set_local_time + project(nx, ny): a pure translation is project_4param_reinit with no rotation / divergence
+    ts = rng.integers(1_000_000_000, 1_200_000_000, n).astype(np.uint64)
+    t0 = 1_050_000_000
+    tl, qx, qy = np.zeros(n, dtype=np.int64), np.zeros(n), np.zeros(n)
+    sl.ev_project(n, _p(fx, C.c_uint32), _p(fy, C.c_uint32), _p(ts, C.c_ulonglong), C.c_ulonglong(t0), C.c_double(0.04),
+                  C.c_double(-0.09), _p(tl, C.c_longlong), _p(qx, C.c_double), _p(qy, C.c_double))
+    assert np.array_equal(tl, ts.astype(np.int64) - t0) and tl.min() < 0 < tl.max()
+    w = oracle_port.project(fx, fy, tl, fx.astype(np.float64), fy.astype(np.float64), 0.04, -0.09, 0.0, 0.0, 0.0, 0.0)
+    assert np.array_equal(qx, w[0]) and np.array_equal(qy, w[1])
