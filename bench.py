@@ -185,6 +185,24 @@ def one_core_baseline(n_slices):
         return None
 
 
+def slice_parallel_baseline(n_slices):
+    """What the host could do with one single-threaded reference process per core, each on its own slices (the
+    slices are independent under --stm-disable; the reference's own tool is one sequential process, so this is a
+    harness around it, reported next to the figure of the reference as it runs).  Children as in one_core_baseline;
+    throughput = all events / the slowest child's run() time."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        cmd = [sys.executable, os.path.abspath(__file__), "--config", CONFIG_NAME, "--cpu-one-core", str(n_slices)]
+        pin = subprocess.run(["taskset", "-c", str(cpus[0]), "true"], capture_output=True).returncode == 0
+        env = dict(os.environ, BF_ORACLE_THREADS="1", OMP_NUM_THREADS="1")
+        procs = [subprocess.Popen((["taskset", "-c", str(c)] if pin else []) + cmd, env=env, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True) for c in cpus]
+        outs = [json.loads(p.communicate(timeout=300)[0].strip().splitlines()[-1]) for p in procs]
+        return {"value": sum(o["events"] for o in outs) / max(o["seconds"] for o in outs) / 1e6, "processes": len(outs)}
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation on the host cores, bounded sample per step."""
     if rank != 0:
@@ -207,7 +225,8 @@ def run_reference_arm(args, rank, world):
         "config": {"workload": WORKLOAD, "sample": "%d slices per step (bounded sample of the same workload)" % per_step,
                    "iters_mean": float(np.mean(its))},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                         "sample": "%d steps x %d slices, OptimizerRolling::run() wall time only" % (args.steps, per_step)},
+                         "sample": "%d steps x %d slices, OptimizerRolling::run() wall time only" % (args.steps, per_step),
+                         "slice_parallel": slice_parallel_baseline(max(1, per_step // 2))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
