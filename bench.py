@@ -2,13 +2,14 @@
 """bench.py -- Mevents/s motion-compensated on B200 (BASELINE.json metric), next to the reference's
 own CPU path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic input: every slice of the batch
 is minimised (OptimizerRolling::run, GD to convergence) by ONE persistent kernel launch.
 Workload = BASELINE.json configs[1]: DAVIS-240C 240x180, 30 ms slices, GD to convergence,
-stm-disabled (independent slices), synthetic 3 Mev/s contour stream (better_flow_b200/synth.py).
+stm-disabled (independent slices), synthetic 3 Mev/s contour stream (better_flow_b200/synth.py);
+--config selects the other BASELINE.json configurations that fit one GPU (CONFIGS below).
 
   value     whole-job Mevents/s with the batch resident in HBM (CUDA events on the launch stream)
   e2e       same through the C ABI with the events in pinned HOST memory: H2D of the events and the
@@ -16,9 +17,12 @@ stm-disabled (independent slices), synthetic 3 Mev/s contour stream (better_flow
   roofline  algorithmic bytes of SURVEY.md 8(d): A = sum_slices iters * (40 N + 16 P), divided by
             the launch duration, against MEASURED_PEAKS.json:hbm_gbs
   cpu_baseline  the reference's unmodified C++ (oracle/_ref, "reference") or its C restatement
-            ("port") timed on this box's host cores on a bounded sample of the same slices
+            ("port") timed on this box's host cores on a bounded sample of the same slices: all
+            threads (value), one pinned core (value_1core)
 At N > 1 every rank minimises its own batch (weak scaling, no data-path collective) and the
-per-slice flow records are gathered with one NCCL all_gather inside the timed region.
+per-slice flow records are gathered with one NCCL all_gather per step inside the timed region
+(on a side stream: the exchange of step k overlaps the minimisation of step k + 1).
+stdout carries exactly one JSON line; everything else (library banners included) goes to stderr.
 """
 from __future__ import annotations
 
