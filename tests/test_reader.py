@@ -115,3 +115,43 @@ def test_from_file_rebases_time_and_swaps_xy(rd, tmp_path):
     want = [0, int(1000000000 * (10.500001 - 10.5)), int(1000000000 * (10.75 - 10.5))]
     assert ts[:3].tolist() == want
     assert fx[:3].tolist() == [3, 4, 5] and fy[:3].tolist() == [7, 8, 9]
+
+
+def test_fast_record_path_never_diverges_from_iostream(rd, tmp_path):
+    """Randomised record shapes around the fast path's acceptance rules (digit counts across the 15-digit limit,
+    bare-dot forms, exponents, signs, tabs, CRLF, blank lines, several blanks, leading zeros, 9/10-digit coordinates):
+    count and every value must equal what `ifstream >>` reads."""
+    rng = np.random.default_rng(20261017)
+
+    def ts():
+        k = rng.integers(0, 8)
+        ip = str(rng.integers(0, 10 ** int(rng.integers(1, 12))))
+        fr = "".join(str(d) for d in rng.integers(0, 10, int(rng.integers(0, 12))))
+        if k == 0: return ip                                  # integer only
+        if k == 1: return ip + "."                            # bare trailing dot
+        if k == 2: return "." + (fr or "5")                   # bare leading dot
+        if k == 3: return "%s.%se%d" % (ip, fr or "0", rng.integers(-5, 6))
+        if k == 4: return "+" + ip + "." + fr
+        if k == 5: return "000" + ip + "." + fr
+        return ip + "." + fr
+
+    def coord():
+        k = rng.integers(0, 10)
+        if k == 0: return str(rng.integers(10 ** 8, 4294967295))   # 9-10 digits
+        if k == 1: return "+" + str(rng.integers(0, 1000))
+        if k == 2: return "00" + str(rng.integers(0, 1000))
+        return str(rng.integers(0, 1280))
+
+    seps = [" ", " ", " ", "  ", "\t", " \t "]
+    eols = ["\n", "\n", "\n", "\r\n", " \n", "\n\n", "\t\n"]
+    lines = []
+    for _ in range(20000):
+        s = lambda: seps[rng.integers(0, len(seps))]
+        lines.append(ts() + s() + coord() + s() + coord() + s() + str(rng.integers(0, 2)) + eols[rng.integers(0, len(eols))])
+    path = tmp_path / "fuzz.txt"
+    path.write_text("".join(lines))
+    a = parse(rd, rd.rd_fast, path, 30000)
+    b = parse(rd, rd.rd_iostream, path, 30000)
+    assert b[0] == 20000
+    same(a, b)
+    same(parse(rd, rd.rd_prefetch, path, 30000), b)
