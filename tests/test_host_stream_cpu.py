@@ -1,0 +1,103 @@
+"""The HOST side of the drop-in against the reference's own DVS_flow, without a GPU: the mirror classes
+(better_flow_b200/include/better_flow: DVS_flow, OptimizerRolling, OptimizerLocal, Event, CircularArray) are linked
+against a test double of the C ABI whose compute is the oracle (tests/cpu/mock_bf_cuda.cpp; the oracle's rolling path
+is pinned bit for bit on the compiled reference), so whatever differs from the reference's per-slice models is a bug in
+the host plumbing: slice hand-over order, local times, warm start through last_model (centre used as stored), noise
+marking, batching of independent slices."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from better_flow_b200 import synth
+from helpers import unhex
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    so = os.path.join(HERE, "cpu", "libstream_shim.so")
+    srcs = [os.path.join(HERE, "cpu", f) for f in ("stream_shim.cpp", "mock_bf_cuda.cpp")]
+    inc = os.path.join(ROOT, "better_flow_b200", "include")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["make", "-s", "-C", odir, "port"])
+    deps = srcs + [os.path.join(inc, "better_flow", f) for f in os.listdir(os.path.join(inc, "better_flow"))] + \
+        [os.path.join(ROOT, "include", "bf_cuda.h"), os.path.join(odir, "libbf_oracle.so")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + inc,
+                               "-I" + os.path.join(ROOT, "include"), *srcs, "-L" + odir, "-lbf_oracle", "-Wl,-rpath," + odir, "-o", so])
+    lib = C.CDLL(so)
+    lib.bf_mock_minimize_calls.restype = C.c_longlong
+    lib.bf_mock_batch_runs.restype = C.c_longlong
+    return lib
+
+
+def run_host(lib, fr_x, fr_y, ts, config=0, ev_refresh=20000, time_refresh_ns=33000000, scale=3, max_iter=-1, stm_disable=False,
+             flush=True, batch=1, local=False, max_slices=512):
+    fx = np.ascontiguousarray(fr_x, dtype=np.uint32)
+    fy = np.ascontiguousarray(fr_y, dtype=np.uint32)
+    t = np.ascontiguousarray(ts, dtype=np.uint64)
+    models = np.zeros((max_slices, 11)); info = np.zeros((max_slices, 3), dtype=np.int64); uv = np.zeros((max_slices, 4))
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    k = lib.st_stream(config, len(fx), p(fx, C.c_uint32), p(fy, C.c_uint32), p(t, C.c_uint64), C.c_ulonglong(ev_refresh),
+                      C.c_ulonglong(time_refresh_ns), scale, max_iter, 1 if stm_disable else 0, 1 if flush else 0, batch,
+                      1 if local else 0, max_slices, p(models, C.c_double), p(info, C.c_longlong), p(uv, C.c_double))
+    assert 0 <= k <= max_slices
+    return models[:k], info[:k], uv[:k]
+
+
+def test_golden_streams_bit_for_bit(hs):
+    """tests/golden: DVS_flow<50000, 200 ms> of the compiled reference, warm-start chain and --stm-disable."""
+    G = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+    EV = np.load(os.path.join(HERE, "golden", "events.npz"))
+    x, y, t = EV["stream_x"], EV["stream_y"], EV["stream_t_ns"].astype(np.uint64)
+    for g in G["streams"]:
+        models, info, _ = run_host(hs, y, x, t, config=g["config"], ev_refresh=g["ev_refresh"], time_refresh_ns=g["time_refresh_ns"],
+                                   scale=g["scale"], max_iter=g["max_iter"], stm_disable=g["stm_disable"])
+        want = np.stack([unhex(m) for m in g["models"]])
+        assert info.tolist() == g["info"]
+        assert models.shape == want.shape
+        assert np.array_equal(models, want), (g["stm_disable"], np.abs(models - want).max())
+
+
+@pytest.mark.parametrize("config,rate,dur,stm_disable,scale,max_iter", [
+    (0, 1.0e6, 0.10, False, 3, 6),        # the tool's configuration, warm-start chain, buffer overflow
+    (0, 1.0e6, 0.10, True, 3, 6),
+    (1, 0.6e6, 0.15, False, 3, 4),        # the ROS node's configuration
+    (0, 0.8e6, 0.08, False, 5, 3),        # scale 5
+    (0, 0.8e6, 0.08, True, 1, 8),         # scale 1
+])
+def test_host_mirror_equals_the_compiled_reference(hs, config, rate, dur, stm_disable, scale, max_iter):
+    from oracle import ref
+    if not ref.available(180, 240):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    st = synth.make_stream(240, 180, rate, dur, seed=60 + config + scale, vel=(70.0, -110.0), omega=0.6, expand=0.3)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    want_models, want_info = ref.stream(fr_x, fr_y, ts, config=config, ev_refresh=15000, time_refresh_ns=25_000_000, scale=scale,
+                                        max_iter=max_iter, stm_disable=stm_disable, flush=True)
+    models, info, uv = run_host(hs, fr_x, fr_y, ts, config=config, ev_refresh=15000, time_refresh_ns=25_000_000, scale=scale,
+                                max_iter=max_iter, stm_disable=stm_disable)
+    assert len(models) == len(want_models) >= 3
+    assert info.tolist() == want_info.tolist()
+    assert np.array_equal(models, want_models), np.abs(models - want_models).max()
+    assert np.all(np.isfinite(uv)) and np.any(uv[:, :2] != 0)       # compute_uv ran over the buffer after every slice
+
+
+def test_batched_independent_slices_equal_unbatched(hs):
+    """--stm-disable --batch=N queues slices and minimises them together: same models, in order, fewer back-end calls."""
+    st = synth.make_stream(240, 180, 1.0e6, 0.12, seed=91)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    c0, b0 = hs.bf_mock_minimize_calls(), hs.bf_mock_batch_runs()
+    a, info, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=True, max_iter=5)
+    c1 = hs.bf_mock_minimize_calls()
+    b, binfo, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=True, max_iter=5, batch=3)
+    assert len(a) == len(b) >= 5 and c1 - c0 == len(a)
+    assert hs.bf_mock_minimize_calls() == c1                         # batched: no per-slice calls ...
+    assert hs.bf_mock_batch_runs() - b0 == -(-len(a) // 3)           # ... but ceil(n / 3) batch runs
+    assert np.array_equal(a, b)
+    assert binfo[:, 1].tolist() == [min(int(i), 49999) if int(i) == 50000 else int(i) for i in info[:, 1]]
