@@ -57,6 +57,11 @@ protected:
         ull slice_start;
     };
     std::vector<Pending> pending_;
+    std::vector<uint16_t> fx_, fy_;          // SoA staging of the slice handed to the back end (reused across slices)
+    std::vector<int32_t> t_;
+    std::vector<uint8_t> nz_;
+    std::vector<double> px_, py_, nx_, ny_;
+    bool lazy_events_ = false;
     int batch_;
     int gpus_;
     bool local_;
@@ -111,6 +116,9 @@ public:
     void set_gpus(int n) { gpus_ = n < 1 ? 1 : n; }
     void set_optimizer_local(bool v = true) { local_ = v; }
     void set_quiet(bool q = true) { quiet_ = q; }
+    // Do not read the per-event state (pr, nx/ny, u/v) back after a slice unless it is being accumulated: the
+    // buffer's events then keep what Event::reset left.  For callers that only want the per-slice models.
+    void set_lazy_events(bool v = true) { lazy_events_ = v; }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
     ObjectModel get_last_model() { return last_model; }
     ull slices_done() const { return slices_done_; }
@@ -165,14 +173,20 @@ template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::add_event(Event 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
     const ull start = slice_start_time();
 
-    LinearEventPtrs e_ptrs;
-    e_ptrs.reserve(ev_buffer.size());
-    for (auto &e : ev_buffer) e_ptrs.push_back(&e);   // newest -> oldest (and SZ-1 elements when full)
-
+    // The slice = what a range-for over the buffer visits: newest -> oldest, and SZ-1 elements when the buffer is
+    // full (dvs_flow.h:196-198 builds a LinearEventPtrs of exactly these).
+    const size_t held = ev_buffer.size();
     SliceLog log;
-    log.size = e_ptrs.size();
-    log.ts_first = log.size ? e_ptrs[0].timestamp : 0;
-    log.ts_last = log.size ? e_ptrs[log.size - 1].timestamp : 0;
+    log.size = held - ((held == ev_buffer.capacity() && held > 0) ? 1 : 0);
+    log.ts_first = log.size ? ev_buffer[0].timestamp : 0;
+    log.ts_last = log.size ? ev_buffer[log.size - 1].timestamp : 0;
+
+    LinearEventPtrs e_ptrs;
+    if (local_ || (batch_ > 1 && stm_disable)) {
+        e_ptrs.reserve(log.size);
+        for (auto &e : ev_buffer) e_ptrs.push_back(&e);
+        assert(e_ptrs.size() == log.size);
+    }
 
     if (local_) {
         // OptimizerLocal works on a LinearEventCloud of its own and never warm-starts
@@ -226,15 +240,60 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
         pending_.push_back(std::move(p));
         if ((int)pending_.size() >= batch_) run_pending();
     } else {
-        OptimizerRolling<LinearEventPtrs> optimizer;
-        optimizer.set_cloud(&e_ptrs, scale);
-        optimizer.set_time(start);
-        optimizer.set_maxiter(max_iter);
-        if (!stm_disable) optimizer.set_model(last_model);   // dvs_flow.h:218-219
-        const int rc = optimizer.run();
-        log.model = optimizer.get_model();
-        for (auto &e : ev_buffer) e.compute_uv();            // dvs_flow.h:234-235
-        log_slice(log, optimizer.iterations(), rc);
+        // The reference's sequence (dvs_flow.h:210-235)
+        //     OptimizerRolling opt; opt.set_cloud(&e_ptrs, scale); opt.set_time(start); opt.set_maxiter(max_iter);
+        //     if (!stm_disable) opt.set_model(last_model); opt.run(); for (e : ev_buffer) e.compute_uv();
+        // touches every 152-byte Event seven times (reset, local time, gather, write-back, assume_score,
+        // compute_uv, plus the pointer vector) -- on the host that costs more than the kernel does.  The same
+        // per-event operations are done here in two passes, in the same order per event; the OptimizerRolling
+        // class itself is unchanged for callers that drive it directly.
+        // (tests/test_host_stream_cpu.py holds both to the reference's DVS_flow and to each other.)
+        const int n = (int)log.size;
+        fx_.resize(n); fy_.resize(n); t_.resize(n); nz_.resize(n);
+        int i = 0;
+        for (auto &e : ev_buffer) {
+            e.reset();                                        // set_cloud (optimizer_rolling.h:262)
+            e.set_local_time(start);                          // set_time (optimizer_rolling.h:241-245)
+            if (e.t > INT32_MAX || e.t < INT32_MIN) {
+                std::cerr << "DVS_flow: local time of an event exceeds +-2.1 s; shorten the slice" << std::endl;
+                std::exit(1);
+            }
+            fx_[i] = (uint16_t)e.fr_x; fy_[i] = (uint16_t)e.fr_y; t_[i] = (int32_t)e.t; nz_[i] = e.noise ? 1 : 0;
+            ++i;
+        }
+        assert(i == n);
+        // per-event state back to the host only when something reads it: the reference always fills it, so the
+        // default is to do so; set_lazy_events() (the CLI without -o) skips the read-back and the second pass
+        const bool want_events = accumulate || !lazy_events_;
+        if (want_events) { px_.resize(n); py_.resize(n); nx_.resize(n); ny_.resize(n); }
+        bf_ctx *ctx = CudaDriver::context(n, 1, scale);
+        const bf_model init = last_model.to_pod();            // set_model(last_model), dvs_flow.h:218-219
+        bf_slice_result res;
+        const int rc = bf_minimize(ctx, fx_.data(), fy_.data(), t_.data(), nz_.data(), n, scale, max_iter,
+                                   stm_disable ? nullptr : &init, &res, want_events ? px_.data() : nullptr,
+                                   want_events ? py_.data() : nullptr, want_events ? nx_.data() : nullptr,
+                                   want_events ? ny_.data() : nullptr);
+        if (rc < 0) {
+            std::cerr << "bf_minimize failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+        if (rc == BF_RC_DEGENERATE)
+            std::cerr << "OptimizerRolling: empty time image (the reference would not terminate here)" << std::endl;
+        log.model.from_pod(res.model);
+        const bool all_noise = (res.flags & BF_FLAG_ALL_NOISE) != 0;   // tiny window (optimizer_rolling.h:49-55)
+        if (want_events) {
+            i = 0;
+            for (auto &e : ev_buffer) {
+                e.pr_x = px_[i]; e.pr_y = py_[i]; e.nx = nx_[i]; e.ny = ny_[i];
+                if (all_noise) e.noise = true;
+                if (rc != BF_RC_SKIPPED) e.assume_score(0);   // optimizer_rolling.h:121-122
+                e.compute_uv();                               // dvs_flow.h:234-235
+                ++i;
+            }
+        } else if (all_noise) {
+            for (auto &e : ev_buffer) e.noise = true;         // (the flag outlives the slice: later slices skip these events)
+        }
+        log_slice(log, res.iters, rc);
         if (accumulate) {                                     // dvs_flow.h:341-346: oldest -> newest copy
             LinearEventCloudTemplate<Event> cur;
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);

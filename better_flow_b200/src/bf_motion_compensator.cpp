@@ -153,6 +153,7 @@ int main(int argc, char *argv[]) {
     DVS_flow<EVENT_WIDTH, FROM_SEC(TIME_WIDTH)> estimator(event_refresh, FROM_SEC(time_refresh), 0, (size_t)max_events,
                                                           (sll)FROM_SEC(slice_time));
     if (outFileName != NULL) estimator.set_accumulate();
+    else estimator.set_lazy_events(true);   // nothing reads the per-event flow: skip its read-back (the per-slice models are unaffected)
     if (manual) estimator.set_manual_mode(true);
     if (img) estimator.set_generate_pictures(true, img_prefix);
     if (video) estimator.set_generate_video(true, video_name, video_fps);

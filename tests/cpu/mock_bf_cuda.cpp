@@ -50,8 +50,16 @@ static void array_to_model(const double *a, bf_model &m) {
     m.total_dx = a[7]; m.total_dy = a[8]; m.total_rot = a[9]; m.total_div = a[10];
 }
 
+static int g_null = 0;   // 1: skip the compute (host-overhead timing of the mirror)
+
 static void run_slice(bf_ctx *c, MockSlice &s) {
     const int n = (int)s.fx.size();
+    if (g_null) {
+        memset(&s.res, 0, sizeof s.res);
+        s.res.n_events = n;
+        s.pr.assign(4 * (size_t)(n > 0 ? n : 1), 0.25);
+        return;
+    }
     double init[11], out[11];
     if (s.has_init) model_to_array(s.init, init);
     std::vector<uint8_t> nz = s.noise;
@@ -83,6 +91,7 @@ const char *bf_last_error(void) { return g_err.c_str(); }
 const char *bf_version(void) { return "mock (oracle back end, tests only)"; }
 long long bf_mock_minimize_calls(void) { return g_minimize_calls; }
 long long bf_mock_batch_runs(void) { return g_batch_runs; }
+void bf_mock_set_null(int v) { g_null = v; }
 
 bf_ctx *bf_ctx_create(int rows, int cols, int, long long, int) {
     bf_ctx *c = new bf_ctx;

@@ -7,6 +7,8 @@
 
 namespace {
 
+constexpr int UV = 14;
+
 template <class Flow> struct FlowProbe : Flow {
     using Flow::Flow;
     size_t remembered() const { return this->motion_memory.size(); }
@@ -21,10 +23,11 @@ void model_out(const ObjectModel &m, double *a) {
 }
 
 // models: 11 doubles per slice; info: 3 per slice = {events consumed, buffer size, buffer time diff} (unbatched runs);
-// uv: 4 doubles per slice = sums of u, v, pr_x, pr_y over the buffer right after the slice (what -o / the viewers read)
+// uv: UV doubles per slice = weighted sums of the per-event fields in the buffer right after the slice (what -o / the viewers read)
 template <class Flow>
 int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint64_t *ts, int scale, int max_iter, int stm_disable,
-        int flush, int batch, int local, int max_slices, double *models, long long *info, double *uv) {
+        int flush, int batch, int local, int lazy, int max_slices, double *models, long long *info, double *uv) {
+    est.set_lazy_events(lazy != 0);
     est.set_scale(scale);
     est.set_max_iter(max_iter);
     est.set_stm_disable(stm_disable != 0);
@@ -38,9 +41,17 @@ int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint
             info[3 * ns + 0] = consumed;
             info[3 * ns + 1] = est.get_buf_size();
             info[3 * ns + 2] = est.get_buf_time_diff();
-            double su = 0, sv = 0, sx = 0, sy = 0;
-            for (auto &e : est.ev_buffer) { su += e.u; sv += e.v; sx += e.pr_x; sy += e.pr_y; }
-            uv[4 * ns + 0] = su; uv[4 * ns + 1] = sv; uv[4 * ns + 2] = sx; uv[4 * ns + 3] = sy;
+            // position-weighted sums of every per-event field the slice leaves behind in the buffer
+            if (uv == nullptr) { ++ns; return; }
+            double c[UV] = {0};
+            double w = 1.0;
+            for (auto &e : est.ev_buffer) {
+                c[0] += w * e.u; c[1] += w * e.v; c[2] += w * e.pr_x; c[3] += w * e.pr_y; c[4] += w * e.nx; c[5] += w * e.ny;
+                c[6] += w * e.best_u; c[7] += w * e.best_v; c[8] += w * e.best_pr_x; c[9] += w * e.best_pr_y;
+                c[10] += w * e.max_score; c[11] += w * (double)e.t; c[12] += e.noise ? w : 0.0; c[13] += 1.0;
+                w += 1e-3;
+            }
+            for (int k = 0; k < UV; ++k) uv[UV * ns + k] = c[k];
         }
         ++ns;
     };
@@ -63,15 +74,15 @@ int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint
 
 extern "C" int st_stream(int config, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint64_t *ts,
                          unsigned long long ev_refresh, unsigned long long time_refresh_ns, int scale, int max_iter, int stm_disable,
-                         int flush, int batch, int local, int max_slices, double *models, long long *info, double *uv) {
+                         int flush, int batch, int local, int lazy, int max_slices, double *models, long long *info, double *uv) {
     bf::set_sensor(180, 240);
     if (config == 0) {
         FlowProbe<DVS_flow<50000, FROM_SEC(0.2)>> est(ev_refresh, time_refresh_ns);
-        return run(est, n, fr_x, fr_y, ts, scale, max_iter, stm_disable, flush, batch, local, max_slices, models, info, uv);
+        return run(est, n, fr_x, fr_y, ts, scale, max_iter, stm_disable, flush, batch, local, lazy, max_slices, models, info, uv);
     }
     if (config == 1) {
         FlowProbe<DVS_flow<30000, FROM_MS(70)>> est(ev_refresh, time_refresh_ns);
-        return run(est, n, fr_x, fr_y, ts, scale, max_iter, stm_disable, flush, batch, local, max_slices, models, info, uv);
+        return run(est, n, fr_x, fr_y, ts, scale, max_iter, stm_disable, flush, batch, local, lazy, max_slices, models, info, uv);
     }
     return -1;
 }

@@ -38,15 +38,15 @@ def hs():
 
 
 def run_host(lib, fr_x, fr_y, ts, config=0, ev_refresh=20000, time_refresh_ns=33000000, scale=3, max_iter=-1, stm_disable=False,
-             flush=True, batch=1, local=False, max_slices=512):
+             flush=True, batch=1, local=False, lazy=False, max_slices=512):
     fx = np.ascontiguousarray(fr_x, dtype=np.uint32)
     fy = np.ascontiguousarray(fr_y, dtype=np.uint32)
     t = np.ascontiguousarray(ts, dtype=np.uint64)
-    models = np.zeros((max_slices, 11)); info = np.zeros((max_slices, 3), dtype=np.int64); uv = np.zeros((max_slices, 4))
+    models = np.zeros((max_slices, 11)); info = np.zeros((max_slices, 3), dtype=np.int64); uv = np.zeros((max_slices, 14))
     p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
     k = lib.st_stream(config, len(fx), p(fx, C.c_uint32), p(fy, C.c_uint32), p(t, C.c_uint64), C.c_ulonglong(ev_refresh),
                       C.c_ulonglong(time_refresh_ns), scale, max_iter, 1 if stm_disable else 0, 1 if flush else 0, batch,
-                      1 if local else 0, max_slices, p(models, C.c_double), p(info, C.c_longlong), p(uv, C.c_double))
+                      1 if local else 0, 1 if lazy else 0, max_slices, p(models, C.c_double), p(info, C.c_longlong), p(uv, C.c_double))
     assert 0 <= k <= max_slices
     return models[:k], info[:k], uv[:k]
 
@@ -101,3 +101,23 @@ def test_batched_independent_slices_equal_unbatched(hs):
     assert hs.bf_mock_batch_runs() - b0 == -(-len(a) // 3)           # ... but ceil(n / 3) batch runs
     assert np.array_equal(a, b)
     assert binfo[:, 1].tolist() == [min(int(i), 49999) if int(i) == 50000 else int(i) for i in info[:, 1]]
+
+
+def test_lazy_events_change_no_model(hs):
+    """set_lazy_events (the CLI without -o): the per-event state is not read back, the per-slice models -- warm-start
+    chain included -- are the same; the tiny-window guard still marks its events as noise for the slices that follow."""
+    st = synth.make_stream(240, 180, 1.0e6, 0.12, seed=33, vel=(-60.0, 90.0))
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    for stm in (False, True):
+        a, ia, uva = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=6)
+        b, ib, uvb = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=6, lazy=True)
+        assert np.array_equal(a, b) and ia.tolist() == ib.tolist()
+        assert np.any(uva[:, 0] != 0) and np.all(uvb[:, 0] == 0) and np.all(uvb[:, 4] == 0)   # u, nx stay as Event::reset left them
+        assert np.array_equal(uva[:, 11:], uvb[:, 11:])                                       # local times, noise flags, counts
+    rng = np.random.default_rng(1)
+    n = 40000
+    fx, fy = rng.integers(80, 88, n), rng.integers(100, 110, n)          # everything inside a tiny window: all-noise guard
+    t = np.sort(rng.integers(10 ** 9, 10 ** 9 + 10 ** 8, n)).astype(np.uint64)
+    a, _, uva = run_host(hs, fx, fy, t, ev_refresh=10000, max_iter=3)
+    b, _, uvb = run_host(hs, fx, fy, t, ev_refresh=10000, max_iter=3, lazy=True)
+    assert np.array_equal(a, b) and np.array_equal(uva[:, 12], uvb[:, 12]) and uva[1, 12] > 0
