@@ -182,7 +182,7 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
     log.ts_last = log.size ? ev_buffer[log.size - 1].timestamp : 0;
 
     LinearEventPtrs e_ptrs;
-    if (local_ || (batch_ > 1 && stm_disable)) {
+    if (local_) {
         e_ptrs.reserve(log.size);
         for (auto &e : ev_buffer) e_ptrs.push_back(&e);
         assert(e_ptrs.size() == log.size);
@@ -220,20 +220,21 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
         // independent slice: snapshot it and minimise later together with its neighbours
         Pending p;
         p.slice_start = start;
-        p.packed.reserve(log.size);
-        for (auto &e : e_ptrs) {
+        p.packed.resize(log.size);
+        size_t k = 0;
+        for (auto &e : ev_buffer) {
             e.reset();
             e.set_local_time(start);
             if (e.t > INT32_MAX || e.t < INT32_MIN) {
                 std::cerr << "DVS_flow: local time of an event exceeds +-2.1 s; shorten the slice" << std::endl;
                 std::exit(1);
             }
-            bf_event b;
+            bf_event &b = p.packed[k++];
             b.fr_x = (uint16_t)e.fr_x;
             b.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u));
             b.t_ns = (int32_t)e.t;
-            p.packed.push_back(b);
         }
+        assert(k == log.size);
         p.log = log;
         if (accumulate)
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) p.copy.push_back(ev_buffer[i]);
