@@ -50,3 +50,62 @@ def test_no_cpu_fallback(cli, tmp_path):
     r = subprocess.run([cli, "--quiet", "--refresh-event-count=1000", str(f)], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stdout + r.stderr)
+
+
+# ---- the whole tool against the reference's tool, on the CPU ----------------------------------------------------
+# bf_motion_compensator.cpp is linked a second time against the oracle-backed test double of the C ABI
+# (tests/cpu/mock_bf_cuda.cpp) instead of the CUDA library.  With an exact back end, everything the tool itself does --
+# parsing, triggers, ring buffer, warm start, per-event flow, accumulation and de-duplication, the -o writer, the
+# per-slice dumps -- must reproduce the reference tool's output byte for byte.
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "bf_motion_compensator_ref")
+
+
+@pytest.fixture(scope="module")
+def mock_cli():
+    exe = os.path.join(ROOT, "tests", "cpu", "bf_motion_compensator_mock")
+    inc = os.path.join(ROOT, "better_flow_b200", "include")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["make", "-s", "-C", odir, "port"])
+    srcs = [os.path.join(ROOT, "better_flow_b200", "src", "bf_motion_compensator.cpp"), os.path.join(ROOT, "tests", "cpu", "mock_bf_cuda.cpp")]
+    deps = srcs + [os.path.join(inc, "better_flow", f) for f in os.listdir(os.path.join(inc, "better_flow"))] + \
+        [os.path.join(ROOT, "include", "bf_cuda.h"), os.path.join(odir, "libbf_oracle.so")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(f) for f in deps):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-pthread", "-I" + inc, "-I" + os.path.join(ROOT, "include"),
+                               *srcs, "-L" + odir, "-lbf_oracle", "-Wl,-rpath," + odir, "-o", exe])
+    return exe
+
+
+def _stable(stdout, *paths):
+    """stdout without the wall-clock lines and with the per-run file names masked."""
+    out = []
+    for l in stdout.splitlines():
+        if "Elapsed:" in l or " sec\t" in l:
+            continue
+        for p in paths:
+            l = l.replace(str(p), "<file>")
+        out.append(l)
+    return out
+
+
+@pytest.mark.parametrize("extra", [[], ["--stm-disable"], ["--refresh-event-count=7000", "--refresh-time=0.011"]])
+def test_tool_with_exact_back_end_equals_the_reference_tool_byte_for_byte(mock_cli, tmp_path, extra):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/bf_motion_compensator_ref not built (no /root/reference here)")
+    from better_flow_b200 import synth
+    st = synth.make_stream(240, 180, 0.7e6, 0.05, seed=17, vel=(90.0, -50.0), omega=0.4)
+    txt = tmp_path / "events.txt"
+    st.to_text(str(txt))
+    o_ref, o_new = tmp_path / "ref_uv.txt", tmp_path / "new_uv.txt"
+    ref = subprocess.run([REF_CLI] + extra + ["-o", str(o_ref), str(txt)], capture_output=True, text=True, timeout=600)
+    new = subprocess.run([mock_cli] + extra + ["-o", str(o_new), str(txt)], capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0 and new.returncode == 0, (ref.stderr[-500:], new.stderr[-1500:])
+    assert open(o_ref, "rb").read() == open(o_new, "rb").read()          # t x y 1 v u for every accumulated event
+    assert os.path.getsize(o_ref) > 100000
+    a, b = _stable(ref.stdout, o_ref, txt), _stable(new.stdout, o_new, txt)
+    assert len(a) > 20 and a == b                                         # per-slice model dumps, accounting lines
+    # without -o the tool skips the per-event read-back (set_lazy_events): the dumps must not change
+    lazy = subprocess.run([mock_cli] + extra + [str(txt)], capture_output=True, text=True, timeout=600)
+    assert lazy.returncode == 0
+    dumps = [l for l in b if l.startswith(("C:", "\t Shift", "\t Rot", "\t Div", "\t cnt"))]
+    assert dumps and dumps == [l for l in _stable(lazy.stdout, txt) if l.startswith(("C:", "\t Shift", "\t Rot", "\t Div", "\t cnt"))]
