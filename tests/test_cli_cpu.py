@@ -109,3 +109,20 @@ def test_tool_with_exact_back_end_equals_the_reference_tool_byte_for_byte(mock_c
     assert lazy.returncode == 0
     dumps = [l for l in b if l.startswith(("C:", "\t Shift", "\t Rot", "\t Div", "\t cnt"))]
     assert dumps and dumps == [l for l in _stable(lazy.stdout, txt) if l.startswith(("C:", "\t Shift", "\t Rot", "\t Div", "\t cnt"))]
+
+
+def test_batched_tool_writes_the_same_flow_file(mock_cli, tmp_path):
+    """--stm-disable --batch=N defers the minimisation of independent slices; the per-event flow written with -o
+    (mapped back from the newest-first slice snapshots) and the per-slice flow lines are those of the unbatched run."""
+    from better_flow_b200 import synth
+    st = synth.make_stream(240, 180, 0.8e6, 0.08, seed=23)
+    txt = tmp_path / "events.txt"
+    st.to_text(str(txt))
+    outs = []
+    for batch in (1, 3):
+        uv, fl = tmp_path / ("uv%d.txt" % batch), tmp_path / ("flow%d.txt" % batch)
+        r = subprocess.run([mock_cli, "--quiet", "--stm-disable", "--max-iter=12", "--refresh-event-count=9000", "--batch=%d" % batch,
+                            "--flow-out=%s" % fl, "-o", str(uv), str(txt)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append((open(uv, "rb").read(), open(fl).read()))
+    assert outs[0] == outs[1] and len(outs[0][1].splitlines()) >= 6 and len(outs[0][0]) > 100000
