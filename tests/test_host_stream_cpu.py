@@ -121,3 +121,29 @@ def test_lazy_events_change_no_model(hs):
     a, _, uva = run_host(hs, fx, fy, t, ev_refresh=10000, max_iter=3)
     b, _, uvb = run_host(hs, fx, fy, t, ev_refresh=10000, max_iter=3, lazy=True)
     assert np.array_equal(a, b) and np.array_equal(uva[:, 12], uvb[:, 12]) and uva[1, 12] > 0
+
+
+def test_optimizer_local_mode_against_the_compiled_class(hs):
+    """--optimizer=local: every slice goes through the OptimizerLocal mirror (cloud copy, run, write-back); the slice
+    model carries -nx, -ny and the score.  Checked against the compiled reference class run on the same slices
+    (reconstructed here from the ring-buffer rules that test_slicing_cpu.py pins)."""
+    from oracle import ref
+    if not ref.available(180, 240):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    st = synth.make_stream(240, 180, 0.5e6, 0.09, seed=71, vel=(120.0, 40.0))
+    fr_x, fr_y, ts = np.asarray(st.y), np.asarray(st.x), np.asarray(st.t_ns).astype(np.int64)
+    models, info, _ = run_host(hs, fr_x, fr_y, ts.astype(np.uint64), ev_refresh=9000, time_refresh_ns=33_000_000, scale=3, local=True)
+    assert len(models) >= 4
+    cap, span = 50000, 200_000_000
+    for m, i in zip(models, info):
+        c = int(i[0])
+        newest = int(ts[c - 1])
+        lo = int(np.searchsorted(ts[:c], newest - span, side="right")) if newest >= span else 0
+        lo = max(lo, c - cap)
+        full = (c - lo) == cap
+        first = lo + (1 if full else 0)
+        start = int(ts[lo]) if full else (newest - span if newest > span else 0)
+        idx = np.arange(c - 1, first - 1, -1)
+        want = ref.local_minimize(fr_x[idx], fr_y[idx], ts[idx] - start, scale=3)
+        assert m[7] == -want["nx"] and m[8] == -want["ny"] and m[2] == want["score"], (i.tolist(), m[7:9], want["nx"], want["ny"])
+    assert np.any(models[:, 7] != 0)
