@@ -399,6 +399,10 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
         for (auto &e : buf) {
             if (e.t == -1) continue;
             for (ull j = i + 1; j < accumulated.size(); ++j) {
+                // buffers are oldest -> newest copies of a ring whose oldest timestamp never decreases: once a
+                // later buffer STARTS after e, neither it nor any buffer after it holds a candidate (o - e <= 0)
+                if (accumulated[j].size() == 0) continue;
+                if (accumulated[j][0] - e > 0) break;
                 auto it = index[j].find(std::make_pair(e.fr_x, e.fr_y));
                 if (it == index[j].end()) continue;
                 for (size_t k : it->second) {

@@ -85,7 +85,10 @@ static void run_slice(bf_ctx *c, MockSlice &s) {
 
 extern "C" {
 
-int bf_cuda_init(int) { return BF_OK; }
+int bf_cuda_init(int) {
+    if (const char *e = std::getenv("BF_MOCK_NULL")) g_null = atoi(e);   // host-overhead timing of the tool: no compute
+    return BF_OK;
+}
 int bf_device_count(void) { return 1; }
 const char *bf_last_error(void) { return g_err.c_str(); }
 const char *bf_version(void) { return "mock (oracle back end, tests only)"; }
