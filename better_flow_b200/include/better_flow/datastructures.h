@@ -117,7 +117,7 @@ public:
         for (auto &d : v) push_back(d);
     }
 
-    void push_back(DType d) {
+    void push_back(const DType &d) {
         grow_box((int)d.get_x(), (int)d.get_y());
         items_.push_back(d);
     }

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 
 #include <better_flow/common.h>
 #include <better_flow/event.h>
@@ -213,8 +214,9 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
         log_slice(log, optimizer.steps(), rc);
         if (accumulate) {
             LinearEventCloudTemplate<Event> cur;
+            cur.reserve(ev_buffer.size());
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);
-            accumulated.push_back(cur);
+            accumulated.push_back(std::move(cur));
         }
     } else if (batch_ > 1 && stm_disable) {
         // independent slice: snapshot it and minimise later together with its neighbours
@@ -236,8 +238,10 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
         }
         assert(k == log.size);
         p.log = log;
-        if (accumulate)
+        if (accumulate) {
+            p.copy.reserve(ev_buffer.size());
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) p.copy.push_back(ev_buffer[i]);
+        }
         pending_.push_back(std::move(p));
         if ((int)pending_.size() >= batch_) run_pending();
     } else {
@@ -297,8 +301,9 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
         log_slice(log, res.iters, rc);
         if (accumulate) {                                     // dvs_flow.h:341-346: oldest -> newest copy
             LinearEventCloudTemplate<Event> cur;
+            cur.reserve(ev_buffer.size());
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);
-            accumulated.push_back(cur);
+            accumulated.push_back(std::move(cur));
         }
     }
     event_diff = 0;
@@ -372,7 +377,7 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
                     if (r.rc != BF_RC_SKIPPED) e.assume_score(0);
                 }
             }
-            accumulated.push_back(p.copy);
+            accumulated.push_back(std::move(p.copy));
         }
     }
     pending_.clear();
@@ -387,12 +392,29 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
     flush();
     LinearEventCloudTemplate<Event> ret;
     std::cout << "Aggregating events into one cloud...\n";
-    typedef std::map<std::pair<uint, uint>, std::vector<size_t>> PixelIndex;
-    std::vector<PixelIndex> index(accumulated.size());
-    for (size_t j = 0; j < accumulated.size(); ++j) {
-        auto &buf = accumulated[j];
-        for (size_t k = 0; k < buf.size(); ++k) index[j][std::make_pair(buf[k].fr_x, buf[k].fr_y)].push_back(k);
-    }
+    // Per-buffer index "pixel -> positions, oldest first" (counting sort by pixel), built when a buffer is first
+    // scanned and dropped once no earlier buffer can reach it any more: a few buffers are alive at a time.
+    struct PixelIndex {
+        std::vector<uint32_t> first, pos;    // first[pixel] .. first[pixel + 1] into pos
+    };
+    uint rows = 1, cols = 1;
+    for (auto &buf : accumulated)
+        for (auto &e : buf) { rows = std::max(rows, e.fr_x + 1); cols = std::max(cols, e.fr_y + 1); }
+    std::vector<std::unique_ptr<PixelIndex>> index(accumulated.size());
+    auto index_of = [&](size_t j) -> const PixelIndex & {
+        if (!index[j]) {
+            auto &buf = accumulated[j];
+            std::unique_ptr<PixelIndex> ix(new PixelIndex);
+            ix->first.assign((size_t)rows * cols + 1, 0u);
+            for (size_t k = 0; k < buf.size(); ++k) ix->first[(size_t)buf[k].fr_x * cols + buf[k].fr_y + 1] += 1;
+            for (size_t p = 1; p < ix->first.size(); ++p) ix->first[p] += ix->first[p - 1];
+            ix->pos.resize(buf.size());
+            std::vector<uint32_t> fill(ix->first.begin(), ix->first.end() - 1);
+            for (size_t k = 0; k < buf.size(); ++k) ix->pos[fill[(size_t)buf[k].fr_x * cols + buf[k].fr_y]++] = (uint32_t)k;
+            index[j] = std::move(ix);
+        }
+        return *index[j];
+    };
     for (ull i = 0; i < accumulated.size(); ++i) {
         std::cout << "\tBuffer: " << i << "\n";
         auto &buf = accumulated[i];
@@ -403,10 +425,10 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
                 // later buffer STARTS after e, neither it nor any buffer after it holds a candidate (o - e <= 0)
                 if (accumulated[j].size() == 0) continue;
                 if (accumulated[j][0] - e > 0) break;
-                auto it = index[j].find(std::make_pair(e.fr_x, e.fr_y));
-                if (it == index[j].end()) continue;
-                for (size_t k : it->second) {
-                    Event &o = accumulated[j][k];
+                const PixelIndex &ix = index_of(j);
+                const size_t pixel = (size_t)e.fr_x * cols + e.fr_y;
+                for (uint32_t q = ix.first[pixel]; q < ix.first[pixel + 1]; ++q) {
+                    Event &o = accumulated[j][ix.pos[q]];
                     if (o - e > 0) continue;      // newer than e: the reference's scan has stopped by then
                     if (o.t == -1) continue;
                     if (e != o) continue;
@@ -415,6 +437,7 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
             }
             ret.push_back(e);
         }
+        index[i].reset();
     }
     std::cout << "FInal buffer contains " << ret.size() << " events." << std::endl;
     return ret;
