@@ -20,8 +20,8 @@ stm-disabled (independent slices), synthetic 3 Mev/s contour stream (better_flow
             ("port") timed on this box's host cores on a bounded sample of the same slices: all
             threads (value), one pinned core (value_1core)
 At N > 1 every rank minimises its own batch (weak scaling, no data-path collective) and the
-per-slice flow records are gathered with one NCCL all_gather per step inside the timed region
-(on a side stream: the exchange of step k overlaps the minimisation of step k + 1).
+per-slice flow records of all timed steps are gathered with ONE NCCL all_gather inside the timed
+region (each step leaves a device-side snapshot of its records; better_flow_b200/shard.py: RecordGather).
 stdout carries exactly one JSON line; everything else (library banners included) goes to stderr.
 """
 from __future__ import annotations
@@ -324,14 +324,15 @@ def main():
     h2d = n_events * 8 + len(slices) * 120   # 8-byte event records + the slice table
     d2h = len(slices) * bf.RESULT_BYTES
 
-    # N > 1: the per-slice flow records of a step are gathered with ONE NCCL all_gather per step.  It runs on a
-    # side stream behind a device-side snapshot of the records, so the exchange of step k overlaps the
-    # minimisation of step k + 1 instead of making all ranks wait for the slowest one at every step.
-    gather_buf = gather_src = side = None
+    # N > 1: every step leaves a device-side snapshot of its per-slice flow records (a stream-ordered ~100 KB D2D
+    # copy), and ONE NCCL all_gather inside the timed region exchanges the records of all its steps
+    # (shard.RecordGather; SURVEY 8e: "one NCCL gather of the resulting flow vectors").  A collective per step made all
+    # ranks wait for the slowest one at every step, and it cannot hide under the next step either: the persistent
+    # kernel holds every register of every SM, so an NCCL kernel only runs in the gap between two launches.
+    rg = None
     if dist is not None:
-        gather_buf = torch.empty(world * len(slices) * bf.RESULT_BYTES, dtype=torch.uint8, device="cuda")
-        gather_src = torch.empty(len(slices) * bf.RESULT_BYTES, dtype=torch.uint8, device="cuda")
-        side = torch.cuda.Stream()
+        from better_flow_b200 import shard
+        rg = shard.RecordGather(dist, torch, len(slices) * bf.RESULT_BYTES, max(args.steps, args.warmup, 1) + 1, "cuda")
 
     class _Dev:  # __cuda_array_interface__ view of the device result records
         def __init__(self, ptr, nbytes):
@@ -341,14 +342,7 @@ def main():
         if dist is None:
             return
         ptr, nbytes = ctx.results_device()
-        mine = torch.as_tensor(_Dev(ptr, nbytes), device="cuda")
-        side.wait_stream(stream)                      # the launch that produced the records
-        with torch.cuda.stream(side):
-            gather_src[:nbytes].copy_(mine, non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(side)
-            dist.all_gather_into_tensor(gather_buf, gather_src)
-        stream.wait_event(copied)                     # the next launch overwrites the records
+        rg.snapshot(torch.as_tensor(_Dev(ptr, nbytes), device="cuda"))   # on the launch stream, before the next launch
 
     def step_resident():
         ctx.launch(False)
@@ -369,8 +363,8 @@ def main():
             e0.record(stream)
             for _ in range(k):
                 fn()
-            if side is not None:
-                stream.wait_stream(side)              # the last gather belongs to the timed region
+            if rg is not None:
+                rg.flush()                            # the one all_gather of these k steps' records: inside the timed region
             e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -384,6 +378,8 @@ def main():
         ctx.upload()
         for _ in range(args.warmup):
             step_resident()
+        if rg is not None:
+            rg.flush()                                # (also creates the NCCL communicator outside the timed region)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -395,6 +391,8 @@ def main():
     launches = ctx.launches - launches0
     with torch.cuda.stream(stream):
         step_e2e()
+        if rg is not None:
+            rg.flush()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     ctx.sync()
@@ -441,7 +439,8 @@ def main():
                        "events_per_step_per_gpu": n_events, "pixels_per_image": P, "iters_mean": float(np.mean(iters)),
                        "iters_max": int(max(iters)), "all_converged": bool(ok), "group_size": ctx.get_option("group_size"),
                        "n_groups": ctx.get_option("n_groups"),
-                       "collective": "one NCCL all_gather of per-slice flow records per step" if world > 1 else "none"},
+                       "collective": ("one NCCL all_gather of the per-slice flow records of the %d timed steps (device snapshot per step), "
+                                      "inside the timed region" % args.steps) if world > 1 else "none"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -73,3 +73,46 @@ def run_sharded(slices, minimise_batch, dist=None, device="cpu", block: int = 4)
     ids = partition(len(slices), world, rank, block)
     results = minimise_batch([slices[i] for i in ids]) if ids else []
     return gather_records(pack_records(ids, results), len(slices), dist, device)
+
+
+class RecordGather:
+    """Deferred gather of the per-slice result records of several batches (bench.py at N > 1).
+
+    Each batch ("step") leaves its rank-local records on the device; `snapshot` copies them into the next slot of a
+    device ring (a stream-ordered D2D copy of ~100 KB), `flush` exchanges every slot taken so far with ONE
+    all_gather.  A collective per step would make all ranks wait for the slowest one at every step -- and cannot
+    overlap the next step either: the persistent minimise kernel holds every register of every SM, so an NCCL
+    kernel only runs in the gap between two launches.  Device-agnostic (CUDA + NCCL in bench.py, CPU + gloo in the
+    tests)."""
+
+    MAX_SLOTS = 256
+
+    def __init__(self, dist, torch, nbytes: int, slots: int, device):
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.nbytes = int(nbytes)
+        self.slots = max(1, min(int(slots), self.MAX_SLOTS))
+        self.ring = torch.empty((self.slots, self.nbytes), dtype=torch.uint8, device=device)
+        self.out = torch.empty(self.world * self.slots * self.nbytes, dtype=torch.uint8, device=device)
+        self.count = 0
+        self.gathers = 0
+        self.last = None
+
+    def snapshot(self, records) -> None:
+        """records: uint8 tensor of nbytes on the ring's device (this rank's bf_slice_result array of one batch)."""
+        if self.count == self.slots:
+            self.flush()
+        self.ring[self.count].copy_(records.reshape(-1)[:self.nbytes], non_blocking=True)
+        self.count += 1
+
+    def flush(self):
+        """ONE all_gather of the snapshots taken since the last flush -> tensor [world, batches, nbytes] (or None)."""
+        if self.count == 0:
+            return None
+        n = self.count
+        dst = self.out[:self.world * n * self.nbytes]
+        self.dist.all_gather_into_tensor(dst, self.ring[:n].reshape(-1))
+        self.count = 0
+        self.gathers += 1
+        self.last = dst.view(self.world, n, self.nbytes)
+        return self.last

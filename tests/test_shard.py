@@ -93,3 +93,52 @@ def test_multi_front_fails_loudly_without_devices():
     with pytest.raises(bf.BfError) as e:
         bf.MultiContext(2, 180, 240, 3, 1 << 16, 8)
     assert "no CPU fallback" in str(e.value)
+
+
+def _gather_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nbytes = 3 * 160                                   # three bf_slice_result records
+    rg = shard.RecordGather(dist, torch, nbytes, slots=4, device="cpu")
+    ok = True
+
+    def batch(step):                                   # what rank `r` leaves on its device after step `s`
+        return lambda r: torch.arange(nbytes, dtype=torch.int64).add(17 * r + 5 * step).remainder(251).to(torch.uint8)
+
+    ok &= rg.flush() is None                           # nothing to exchange yet: no collective
+    for step in range(3):
+        rg.snapshot(batch(step)(rank))
+    got = rg.flush()
+    ok &= rg.gathers == 1 and tuple(got.shape) == (world, 3, nbytes)
+    for r in range(world):
+        for step in range(3):
+            ok &= bool(torch.equal(got[r, step], batch(step)(r)))
+    # more batches than slots: the ring is flushed when it is full, then once more at the end
+    for step in range(6):
+        rg.snapshot(batch(10 + step)(rank))
+    got = rg.flush()
+    ok &= rg.gathers == 3 and tuple(got.shape) == (world, 2, nbytes)
+    for r in range(world):
+        ok &= bool(torch.equal(got[r, 0], batch(14)(r))) and bool(torch.equal(got[r, 1], batch(15)(r)))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_deferred_record_gather_two_ranks():
+    """bench.py at N > 1: per-step device snapshots of the result records, ONE all_gather for all of them."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
