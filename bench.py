@@ -338,11 +338,21 @@ def main():
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
+    fallback = {"buf": None}   # set if the deferred gather cannot be used: one in-line all_gather per step instead
+
     def gather():
         if dist is None:
             return
         ptr, nbytes = ctx.results_device()
-        rg.snapshot(torch.as_tensor(_Dev(ptr, nbytes), device="cuda"))   # on the launch stream, before the next launch
+        mine = torch.as_tensor(_Dev(ptr, nbytes), device="cuda")
+        if fallback["buf"] is not None:
+            dist.all_gather_into_tensor(fallback["buf"], mine)
+            return
+        rg.snapshot(mine)                             # on the launch stream, before the next launch
+
+    def flush_gather():
+        if rg is not None and fallback["buf"] is None:
+            rg.flush()
 
     def step_resident():
         ctx.launch(False)
@@ -363,8 +373,7 @@ def main():
             e0.record(stream)
             for _ in range(k):
                 fn()
-            if rg is not None:
-                rg.flush()                            # the one all_gather of these k steps' records: inside the timed region
+            flush_gather()                            # the one all_gather of these k steps' records: inside the timed region
             e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -376,10 +385,17 @@ def main():
 
     with torch.cuda.stream(stream):
         ctx.upload()
-        for _ in range(args.warmup):
-            step_resident()
-        if rg is not None:
-            rg.flush()                                # (also creates the NCCL communicator outside the timed region)
+        try:
+            for _ in range(args.warmup):
+                step_resident()
+            flush_gather()                            # (also creates the NCCL communicator outside the timed region)
+        except Exception as exc:                      # same code and shapes on every rank: they all land here together
+            if rg is None:
+                raise
+            print("deferred record gather unavailable (%s): one all_gather per step instead" % exc, file=sys.stderr)
+            fallback["buf"] = torch.empty(world * len(slices) * bf.RESULT_BYTES, dtype=torch.uint8, device="cuda")
+            for _ in range(args.warmup):
+                step_resident()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -391,8 +407,7 @@ def main():
     launches = ctx.launches - launches0
     with torch.cuda.stream(stream):
         step_e2e()
-        if rg is not None:
-            rg.flush()
+        flush_gather()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     ctx.sync()
@@ -439,8 +454,10 @@ def main():
                        "events_per_step_per_gpu": n_events, "pixels_per_image": P, "iters_mean": float(np.mean(iters)),
                        "iters_max": int(max(iters)), "all_converged": bool(ok), "group_size": ctx.get_option("group_size"),
                        "n_groups": ctx.get_option("n_groups"),
-                       "collective": ("one NCCL all_gather of the per-slice flow records of the %d timed steps (device snapshot per step), "
-                                      "inside the timed region" % args.steps) if world > 1 else "none"},
+                       "collective": "none" if world == 1 else
+                                     ("one NCCL all_gather of per-slice flow records per step" if fallback["buf"] is not None else
+                                      "one NCCL all_gather of the per-slice flow records of the %d timed steps (device snapshot per step), "
+                                      "inside the timed region" % args.steps)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
