@@ -381,8 +381,10 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             const int s = atomicAdd(P.queue, 1);
             // streamed upload: the copy engine is still filling the event buffer in slice order; wait
             // until this slice has landed (the counter is written by a copy that follows the data)
-            if (P.ready != nullptr && s < P.n_slices)
+            if (P.ready != nullptr && s < P.n_slices) {
                 while (ld_relaxed_u32(P.ready) <= (unsigned)s) __nanosleep(200);
+                fence_acq_rel_gpu();   // acquire: the copy engine wrote the slice's events before it bumped the counter
+            }
             int *bb = ws->bbox[parity];
             bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; bb[4] = INT_MAX; bb[5] = INT_MIN;
             ws->cur_slice = s;
@@ -678,9 +680,16 @@ struct bf_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D of the streamed upload
-    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
-    unsigned *d_ready = nullptr;          // slices uploaded so far (device), fed from h_ready (pinned)
-    unsigned *h_ready = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};   // recorded behind the last launch that read event buffer 0 / 1
+    unsigned *d_ready = nullptr;          // [2][64]: slices uploaded so far (device, one counter per event buffer), fed from h_ready
+    unsigned *h_ready = nullptr;          // [2][64] pinned
+    // Two device copies of the batch (events + slice table): bf_batch_run_streamed fills the one the previous launch is
+    // NOT reading, so the H2D of batch k+1 runs under the kernel of batch k.  `d_events` / `d_slices` below always point
+    // at the current one; the second copy is allocated at the first streamed run.
+    bf_event *ev_buf[2] = {nullptr, nullptr};
+    struct SliceDesc *sl_buf[2] = {nullptr, nullptr};
+    int cur = 0;
     int upload_chunks = 32;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -884,9 +893,10 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     c->stream = c->own_stream;
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaMalloc(&c->d_ready, 256)) != cudaSuccess) return bail("cudaMalloc(ready)", e);
-    if ((e = cudaMallocHost(&c->h_ready, 64 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMallocHost(ready)", e);
+    for (int b = 0; b < 2; ++b)
+        if ((e = cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&c->d_ready, 2 * 64 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc(ready)", e);
+    if ((e = cudaMallocHost(&c->h_ready, 2 * 64 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMallocHost(ready)", e);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
 
@@ -905,8 +915,11 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     if ((e = cudaMallocHost(&c->h_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMallocHost(results)", e);
     // (+2: the event pass reads events / states in aligned pairs, so the pair holding the last event is read whole)
     if ((e = cudaMalloc(&c->d_events, (size_t)(max_events + 2) * sizeof(bf_event))) != cudaSuccess) return bail("cudaMalloc(events)", e);
+    // (never hand uninitialised coordinates to the kernel: the pair / sector holding a slice's last event is read whole)
+    if ((e = cudaMemset(c->d_events, 0, (size_t)(max_events + 2) * sizeof(bf_event))) != cudaSuccess) return bail("cudaMemset(events)", e);
     if ((e = cudaMalloc(&c->d_state, (size_t)(max_events + 2) * sizeof(float2))) != cudaSuccess) return bail("cudaMalloc(state)", e);
     if ((e = cudaMalloc(&c->d_slices, (size_t)max_slices * sizeof(SliceDesc))) != cudaSuccess) return bail("cudaMalloc(slices)", e);
+    c->ev_buf[0] = c->d_events; c->sl_buf[0] = c->d_slices;
     if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
 
     if (smem_bytes_min(c) > 100 * 1024) {
@@ -914,8 +927,10 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
         bf_ctx_destroy(c);
         return nullptr;
     }
-    // (the attribute is per function, not per context: only ever raise it)
-    static int smem_attr = 0;
+    // The attribute is per function AND per device (not per context): only ever raise it, and keep one
+    // high-water mark per device -- bf_multi_create makes a context on every device of the process.
+    static int smem_attr_of[64] = {0};
+    int &smem_attr = smem_attr_of[c->device & 63];
     if ((int)smem_bytes_min(c) > smem_attr) {
         smem_attr = (int)smem_bytes_min(c);
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
@@ -935,7 +950,8 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
-    cudaFree(c->d_events); cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy); cudaFree(c->d_slices);
+    cudaFree(c->ev_buf[0]); cudaFree(c->ev_buf[1]); cudaFree(c->sl_buf[0]); cudaFree(c->sl_buf[1]);
+    cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy);
     cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
     cudaFree(c->d_stage); cudaFree(c->d_prof); cudaFree(c->d_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -943,7 +959,8 @@ void bf_ctx_destroy(bf_ctx *c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
-    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (int b = 0; b < 2; ++b)
+        if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
     cudaFree(c->d_ready); cudaFreeHost(c->h_ready);
     delete c;
 }
@@ -1120,16 +1137,25 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
 // upload -> launch -> download with the event upload STREAMED: the slice table goes first, the kernel
 // is launched at once, and the events follow in slice-ordered chunks on a second stream while the
 // first slices are already being minimised (each chunk is followed by a 4-byte copy that bumps the
-// device-side "slices uploaded" counter the kernel polls).  Asynchronous; pair with bf_batch_sync.
+// device-side "slices uploaded" counter the kernel polls).  The upload goes into the device copy of the
+// batch that the PREVIOUS launch is not reading (two copies, ping-pong), so back-to-back streamed runs
+// overlap the H2D of batch k+1 with the kernel of batch k.  Asynchronous; pair with bf_batch_sync (and
+// do not touch the staging buffer before that).
 int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     if (!c) return fail(BF_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     if (c->n_slices == 0) { c->uploaded = c->ran = true; return BF_OK; }
-    // the copy stream must not overtake work still queued on the compute stream (previous batch)
-    CU(cudaEventRecord(c->ev_done, c->stream));
-    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
-    CU(cudaMemsetAsync(c->d_ready, 0, sizeof(unsigned), c->copy_stream));
-    CU(cudaMemcpyAsync(c->d_slices, c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
+    const int nb = c->cur ^ 1;
+    if (!c->ev_buf[nb]) {
+        CU(cudaMalloc(&c->ev_buf[nb], (size_t)(c->max_events + 2) * sizeof(bf_event)));
+        CU(cudaMemset(c->ev_buf[nb], 0, (size_t)(c->max_events + 2) * sizeof(bf_event)));
+        CU(cudaMalloc(&c->sl_buf[nb], (size_t)c->max_slices * sizeof(SliceDesc)));
+    }
+    unsigned *d_ready = c->d_ready + 64 * nb, *h_ready = c->h_ready + 64 * nb;
+    // the copy engine must not write this buffer before the last launch that read it has finished
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[nb], 0));
+    CU(cudaMemsetAsync(d_ready, 0, sizeof(unsigned), c->copy_stream));
+    CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copy, c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     // chunk boundaries on slice boundaries (slices are laid out back to back in add order)
@@ -1141,13 +1167,16 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
         const long long lo = c->h_slices[s0].ev_off;
         const long long hi = c->h_slices[s1 - 1].ev_off + c->h_slices[s1 - 1].n;
         if (hi > lo)
-            CU(cudaMemcpyAsync(c->d_events + lo, c->h_events + lo, (size_t)(hi - lo) * sizeof(bf_event), cudaMemcpyHostToDevice, c->copy_stream));
-        c->h_ready[k] = (unsigned)s1;
-        CU(cudaMemcpyAsync(c->d_ready, c->h_ready + k, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaMemcpyAsync(c->ev_buf[nb] + lo, c->h_events + lo, (size_t)(hi - lo) * sizeof(bf_event), cudaMemcpyHostToDevice, c->copy_stream));
+        h_ready[k] = (unsigned)s1;
+        CU(cudaMemcpyAsync(d_ready, h_ready + k, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
         s0 = s1;
     }
+    c->cur = nb;
+    c->d_events = c->ev_buf[nb];
+    c->d_slices = c->sl_buf[nb];
     c->uploaded = true;
-    int rc = launch_impl(c, want_events, c->d_ready);
+    int rc = launch_impl(c, want_events, d_ready);
     if (rc != BF_OK) return rc;
     return bf_batch_download(c);
 }
@@ -1200,6 +1229,7 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     if (c->ctas_per_sm == 4) kern = (void *)bf_minimize_kernel<4>;
 #endif
     CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
+    CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this)
     c->launches += 1;
     c->ran = true;
     c->have_events = want_events != 0;

@@ -171,12 +171,29 @@ __device__ __forceinline__ void red_add_u64(u64 *p, u64 v) {
 #define BF_EVICT 1             // event / state streams are loaded / stored with the streaming (.cs, L2 evict-first) hint: 426 MB of
                                // each pass through L2 per iteration and would otherwise push out the images (+0.8 %, same-box A/B)
 #endif
+// EVENT LOADS.  The event buffer is read-only for the kernel EXCEPT under the streamed upload
+// (bf_batch_run_streamed), where the copy engine is still filling it in slice order while the kernel works on
+// the slices that have landed.  A 32-byte sector (4 events) can straddle two slices, so a load that allocates in
+// L1 (ld.global.nc, LDG.E.CONSTANT) may cache the not-yet-written first events of the NEXT slice, and a CTA that
+// later minimises that slice on the same SM could hit the stale sector.  Events are therefore loaded L2-coherent
+// (ld.global.cg = LDG.E.STRONG.GPU: never served from L1); nothing is lost, an event is read once per iteration by
+// one thread, so L1 never had a hit to offer.  BF_EV_LD selects the variant for same-box A/B runs:
+//   0  ld.global.cs.nc   (round 1: L1-allocating, evict-first; unsafe under the streamed upload)
+//   1  ld.global.cg      (L2-coherent; default)
+//   2  ld.relaxed.gpu + createpolicy L2::evict_first  (L2-coherent and evict-first in L2)
+#ifndef BF_EV_LD
+#define BF_EV_LD 1
+#endif
 __device__ __forceinline__ uint4 ld_nc_u32x4(const void *p) {
     uint4 v;
-#if BF_EVICT
+#if BF_EV_LD == 0
     asm volatile("ld.global.cs.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#elif BF_EV_LD == 2
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
 #else
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
 #endif
     return v;
 }
@@ -196,9 +213,13 @@ __device__ __forceinline__ void st_state4(float4 *p, float4 v) {
 #endif
 }
 
-__device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {
+__device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {   // (one event; same coherence rule as ld_nc_u32x4)
     uint2 v;
+#if BF_EV_LD == 0
     asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#else
+    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#endif
     return v;
 }
 

@@ -116,3 +116,44 @@ class RecordGather:
         self.gathers += 1
         self.last = dst.view(self.world, n, self.nbytes)
         return self.last
+
+
+def deal_pool(local_events, dist, torch, device, block: int = 4):
+    """Pooled block-cyclic deal of a weak-scaling batch (bench.py at N > 1).
+
+    Every rank brings the packed 8-byte event records of S slices (``local_events``: list of S numpy arrays of
+    better_flow_b200.EVENT_DTYPE).  The POOL is the rank-major concatenation of all ranks' lists -- world * S
+    slices -- and it is dealt with `partition` (blocks of `block` consecutive pool slices, round-robin), so every
+    rank ends up with S slices drawn evenly from all ranks' streams: iteration counts depend on a stream's contour
+    geometry, and a rank that kept its own stream would carry that stream's bias for the whole run (round 1:
+    +12 % GD iterations on one rank of eight set the max-over-ranks time).  Set-up plumbing, outside any timed region:
+    two all_gathers (slice lengths, padded event bytes), then each rank cuts its share out of the gathered pool on
+    `device`.  Returns (global pool ids, list of numpy EVENT_DTYPE arrays) for this rank."""
+    from . import EVENT_DTYPE
+    world, rank = dist.get_world_size(), dist.get_rank()
+    S = len(local_events)
+    lens = torch.tensor([len(e) for e in local_events], dtype=torch.int64, device=device)
+    all_lens = torch.empty((world, S), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_lens.view(-1), lens)            # (same S on every rank: the collective checks sizes)
+    cap = int(all_lens.sum(dim=1).max().item())
+    mine = torch.zeros(cap * 8, dtype=torch.uint8, device=device)
+    flat = np.concatenate(local_events) if S else np.zeros(0, dtype=EVENT_DTYPE)
+    mine[:flat.nbytes] = torch.from_numpy(flat.view(np.uint8).copy()).to(device)
+    pool = torch.empty((world, cap * 8), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(pool.view(-1), mine)
+    offs = torch.cumsum(all_lens, dim=1) - all_lens                   # first event of every pool slice in its source buffer
+    all_lens_h, offs_h = all_lens.cpu().numpy(), offs.cpu().numpy()
+    ids = partition(world * S, world, rank, block)
+    parts = []
+    for g in ids:
+        src, i = divmod(g, S)
+        o, n = int(offs_h[src, i]), int(all_lens_h[src, i])
+        parts.append(pool[src, o * 8:(o + n) * 8])
+    got = (torch.cat(parts) if parts else mine[:0]).cpu().numpy().view(EVENT_DTYPE)
+    out, k = [], 0
+    for g in ids:
+        src, i = divmod(g, S)
+        n = int(all_lens_h[src, i])
+        out.append(got[k:k + n])
+        k += n
+    return ids, out

@@ -62,3 +62,20 @@ def same_model(a, b, rtol=1e-12):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return a[6] == b[6] and bool(np.allclose(a, b, rtol=rtol, atol=0))
+
+
+def ring_slice(ts, consumed, capacity=50000, span_ns=200_000_000):
+    """The events DVS_flow<capacity, span>::recompute hands to the optimiser after `consumed` events of a stream
+    with timestamps `ts` (ns, non-decreasing): indices newest -> oldest and the slice start time -- the ring buffer
+    with its lazy eviction and its full-buffer quirk restated (datastructures.h:31-96, dvs_flow.h:186-198; the same
+    restatement tests/test_slicing_cpu.py pins against the compiled reference)."""
+    ts = np.asarray(ts).astype(np.int64)
+    c = int(consumed)
+    newest = int(ts[c - 1])
+    lo = int(np.searchsorted(ts[:c], newest - span_ns, side="right")) if newest >= span_ns else 0
+    lo = max(lo, c - capacity)
+    full = (c - lo) == capacity
+    first = lo + (1 if full else 0)
+    idx = np.arange(c - 1, first - 1, -1)
+    start = int(ts[lo]) if full else (newest - span_ns if newest > span_ns else 0)
+    return idx, start

@@ -122,6 +122,7 @@ def _stub_worker(rank, world, port, q, break_gather):
     torch.empty, torch.tensor = on_cpu(real_empty), on_cpu(real_tensor)
 
     calls = {"launch": 0, "streamed": 0, "gathers": 0}
+    dealt = []
 
     class FakeContext:
         launches = 0
@@ -136,7 +137,9 @@ def _stub_worker(rank, world, port, q, break_gather):
         def set_stream(self, s): pass
         def staging(self): return self.buf
         def reset(self): self.sl = []
-        def add_staged(self, off, n, scale, max_iter): self.sl.append(n)
+        def add_staged(self, off, n, scale, max_iter):
+            self.sl.append(n)
+            dealt.append(self.buf[off:off + n].copy())
         def upload(self): pass
         def sync(self): pass
         def close(self): pass
@@ -152,7 +155,7 @@ def _stub_worker(rank, world, port, q, break_gather):
         def results_device(self): return 0, len(self.sl) * bf.RESULT_BYTES
 
         def results(self):
-            return [{"rc": 0, "iters": 10 + rank, "n_events": n, "img_rows": 543, "img_cols": 723} for n in self.sl]
+            return [{"rc": 0, "iters": 10 + rank, "n_events": n, "img_rows": 543, "img_cols": 723, "model": np.zeros(11)} for n in self.sl]
 
     bf.Context = FakeContext
     fake_ctx_holder = {}
@@ -163,6 +166,7 @@ def _stub_worker(rank, world, port, q, break_gather):
         fake_ctx_holder["ctx"] = self
     FakeContext.__init__ = init
     torch.as_tensor = lambda obj, **k: fake_ctx_holder["ctx"].rec if hasattr(obj, "__cuda_array_interface__") else real_as_tensor(obj)
+    bench.DEV = "cpu"
 
     real_init_pg = dist.init_process_group
     dist.init_process_group = lambda backend, **k: real_init_pg("gloo", rank=rank, world_size=world)
@@ -185,6 +189,13 @@ def _stub_worker(rank, world, port, q, break_gather):
     bench.quiet_stdout = lambda: None
     sys.argv = ["bench.py", "--gpus", str(world), "--steps", "4", "--warmup", "3", "--slices", "3", "--cpu-sample", "0"]
     bench.main()
+    # the pooled deal: this rank must hold pool slices shard.partition(2 * 3, 2, rank, 4) of the rank-major pool
+    pool = []
+    for r in range(world):
+        pool += [bf.pack_events(s.fr_x, s.fr_y, s.t_ns) for s in bench.make_batch(100 + r, 3)]
+    want = [pool[g] for g in shard.partition(world * 3, world, rank, 4)]
+    calls["deal_ok"] = len(want) == len(dealt) and all(np.array_equal(a, b) for a, b in zip(want, dealt))
+    calls["n_dealt"] = len(dealt)
     q.put((rank, lines, calls))
 
 
@@ -205,7 +216,11 @@ def test_product_arm_control_flow_two_ranks_with_stubs(break_gather):
     assert len(res[0][0]) == 1 and res[1][0] == []                      # rank 0 prints the one line, rank 1 nothing
     d = res[0][0][0]
     assert d["n_gpus"] == 2 and d["steps"] == 4 and d["warmup"] == 3 and d["gpu_launches"] == 4
-    assert d["config"]["events_per_step_per_gpu"] > 200000 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["config"]["events_per_step_per_gpu"] > 80000 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["scaling"] == "weak" and "dealt block-cyclically" in d["config"]["partition"]
+    assert d["gather_ok"] is True and [p["rank"] for p in d["per_rank"]] == [0, 1]
+    assert [p["slices"] for p in d["per_rank"]] == [4, 2] and d["per_rank"][1]["sum_iters"] == 2 * 11
+    assert res[0][1]["deal_ok"] and res[1][1]["deal_ok"]
     for r in (0, 1):
         calls = res[r][1]
         assert calls["streamed"] == 5                                   # one warm e2e step + 4 timed
@@ -215,5 +230,5 @@ def test_product_arm_control_flow_two_ranks_with_stubs(break_gather):
         else:
             assert calls["launch"] == 3 + 4
             assert calls["gathers"] == 4                                # warm-up, timed resident, warm e2e, timed e2e
-            assert calls["last_shape"] == (2, 4, 3 * 160) and calls["last_ok"]
+            assert calls["last_shape"] == (2, 4, 4 * 160) and calls["last_ok"]
             assert "4 timed steps" in d["config"]["collective"]

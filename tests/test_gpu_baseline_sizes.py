@@ -107,3 +107,64 @@ def test_config3_vga_sharded_batch_is_order_and_grouping_independent():
         for a, b in zip(outs[0], other):
             assert a[0] == b[0] and a[1] == b[1]
             assert np.all(rel(a[2:], b[2:]) < 1e-10)      # only the fp64 reduction tree differs with G
+
+
+# ---- the BASELINE shapes at the setting bench.py runs them: GD to convergence, against the REFERENCE arithmetic ----
+# (oracle mode 0 is bit-equal to the compiled reference, tests/test_oracle.py; optimizer_rolling.h:48-125)
+
+def _check_convergence(c, sls, rows, cols, max_iter, oracle_port, picks):
+    for s in sls:
+        c.add(s.fr_x, s.fr_y, s.t_ns, 3, max_iter)
+    c.run()
+    res = c.results()
+    assert all(r["rc"] == 0 for r in res)
+    worst = 0.0
+    for k in picks:
+        s = sls[k]
+        ref = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=max_iter, rows=rows, cols=cols, accum_mode=0)
+        exact = oracle_port.minimize(s.fr_x, s.fr_y, s.t_ns, scale=3, max_iter=max_iter, rows=rows, cols=cols, accum_mode=1)
+        got = res[k]
+        assert got["iters"] == exact["iters"] and got["model"][6] == exact["model"][6]
+        assert got["dividers"].tobytes() == exact["dividers"].tobytes()
+        assert np.all(rel(got["model"][7:11], exact["model"][7:11]) < 1e-9)
+        d = float(np.max(rel(got["model"][7:9], ref["model"][7:9])))
+        worst = max(worst, d)
+        assert d < 1e-4, (k, d, got["iters"], ref["iters"])                    # the contract, vs the reference arithmetic
+    return worst
+
+
+def test_config2_davis346_to_convergence_vs_reference_arithmetic(oracle_port):
+    """configs[2] as benchmarked: DAVIS-346, 50 ms slices (~100 k events), 64 slices per launch, max_iter = -1."""
+    st = synth.make_stream(346, 260, 2e6, 0.05 * 64, seed=33)
+    sls = synth.cut_slices(st, 0.05)[:64]
+    c = bf.Context(260, 346, 3, max_events=sum(len(s.fr_x) for s in sls) + 16, max_slices=65, device=0)
+    try:
+        worst = _check_convergence(c, sls, 260, 346, -1, oracle_port, (0, 9, 21, 38, 50, 63))
+        print("cfg3 to convergence: max rel (dx,dy) vs reference arithmetic %.3g" % worst)
+    finally:
+        c.close()
+
+
+def test_config3_vga_to_convergence_vs_reference_arithmetic(oracle_port):
+    """configs[3] as benchmarked: 640x480, 20 ms slices (200 k events), max_iter = -1."""
+    st = synth.make_stream(640, 480, 10e6, 0.02 * 6, seed=55)
+    sls = synth.cut_slices(st, 0.02)[:6]
+    c = bf.Context(480, 640, 3, max_events=sum(len(s.fr_x) for s in sls) + 16, max_slices=7, device=0)
+    try:
+        worst = _check_convergence(c, sls, 480, 640, -1, oracle_port, (0, 3, 5))
+        print("cfg4 to convergence: max rel (dx,dy) vs reference arithmetic %.3g" % worst)
+    finally:
+        c.close()
+
+
+def test_config4_hd_ten_iterations_vs_reference_arithmetic(oracle_port):
+    """configs[4] shape: 1280x720, 1 M events; 10 GD iterations (11 steps) against the reference arithmetic (the
+    oracle needs ~4 s per mode at this size; to convergence it would need minutes)."""
+    st = synth.make_stream(1280, 720, 100e6, 0.01, seed=44)
+    sls = synth.cut_slices(st, 0.01)[:1]
+    c = bf.Context(720, 1280, 3, max_events=len(sls[0].fr_x) + 16, max_slices=2, device=0)
+    try:
+        worst = _check_convergence(c, sls, 720, 1280, 10, oracle_port, (0,))
+        print("cfg5, 10 iterations: max rel (dx,dy) vs reference arithmetic %.3g" % worst)
+    finally:
+        c.close()

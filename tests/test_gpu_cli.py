@@ -82,8 +82,10 @@ def test_cli_matches_golden_dvs_flow_streams(cli, tmp_path):
         # Independent slices meet the 1e-4 contract.  A warm-start CHAIN compounds per-slice differences:
         # slice 1 of this stream is a knife-edge case on which the reference itself moves by 5.4e-5 when
         # its events are merely fed oldest-first (f32 accumulation order, DESIGN.md "Numerics"), and the
-        # following slices inherit that through last_model, so the chain is held to 2e-3 instead.
-        tol = 1e-4 if g["stm_disable"] else 2e-3
+        # following slices inherit that through last_model.  Measured free-running deviation of this chain: 2.9e-4
+        # (exact-sum oracle and GPU alike, test_warm_start_chain_slice_by_slice_golden prints it); the chain is held
+        # to twice that.  Slice by slice, seeded with the reference's own last_model, every slice meets 1e-4 (below).
+        tol = 1e-4 if g["stm_disable"] else 6e-4
         assert np.all(rel < tol), rel
         assert np.all(rel[0] < 1e-6)
         if g["stm_disable"]:
@@ -127,3 +129,70 @@ def test_cli_batch_mode_equals_unbatched(cli, tmp_path):
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append(open(out).read())
     assert outs[0] == outs[1] and len(outs[0].splitlines()) >= 8
+
+
+# ---- warm-start chains, slice by slice ----------------------------------------------------------------------
+# A warm-start chain compounds per-slice differences through last_model, so the free-running chain is a weak
+# test of the contract.  Here every slice of a chain is minimised on the GPU from the REFERENCE's own last_model
+# (set_model, optimizer_rolling.h:289-299) and held to the 1e-4 contract on its own; the free-running chain's
+# actual deviation is measured next to it.
+
+def _chain_case(fr_x, fr_y, ts, models, info, max_iter, ctx):
+    """-> (per-slice relative deviation when seeded with the reference's last_model, free-running deviation)."""
+    from helpers import ring_slice
+    seeded, free = [], []
+    last_free = None
+    for k, (m, i) in enumerate(zip(models, info)):
+        idx, start = ring_slice(ts, i[0])
+        t_loc = (ts[idx].astype(np.int64) - start).astype(np.int32)
+        init = models[k - 1] if k > 0 else None
+        got = ctx.minimize(fr_x[idx], fr_y[idx], t_loc, 3, max_iter, init=init)
+        seeded.append(np.max(np.abs(got["model"][7:9] - m[7:9]) / np.abs(m[7:9])))
+        run = ctx.minimize(fr_x[idx], fr_y[idx], t_loc, 3, max_iter, init=last_free)
+        last_free = run["model"]
+        free.append(np.max(np.abs(run["model"][7:9] - m[7:9]) / np.abs(m[7:9])))
+    return np.array(seeded), np.array(free)
+
+
+def test_warm_start_chain_slice_by_slice_golden(ctx240):
+    G, EV = golden()
+    g = [s for s in G["streams"] if not s["stm_disable"]][0]
+    fr_x, fr_y, ts = EV["stream_y"], EV["stream_x"], EV["stream_t_ns"].astype(np.int64)   # Event(y, x, t): fr_x = row
+    models = [unhex(m) for m in g["models"]]
+    seeded, free = _chain_case(fr_x, fr_y, ts, models, g["info"], g["max_iter"], ctx240)
+    print("golden warm-start chain: seeded max rel %.3g, free-running max rel %.3g" % (seeded.max(), free.max()))
+    assert np.all(seeded < 1e-4), seeded
+
+
+def test_warm_start_chain_slice_by_slice_against_reference(ctx240, oracle_port):
+    """A longer chain (GD to convergence, 23 overlapping windows of up to 50 k events, rotating scene) against the
+    compiled reference's DVS_flow, when oracle/_ref travelled with the snapshot.  Every slice, seeded with the
+    reference's last_model, must meet the 1e-4 contract -- unless the slice is demonstrably ill-conditioned at that
+    level: the reference's own arithmetic (oracle mode 0, bit-equal to the compiled reference) moves by more than
+    2.5e-5 when its events are merely fed in another order.  At most one slice in ten may take that exit."""
+    from oracle import ref
+    from helpers import ring_slice
+    if not ref.available(180, 240):
+        pytest.skip("oracle/_ref not present in this snapshot")
+    st = synth.make_stream(240, 180, 1.5e6, 0.3, seed=77, vel=(60.0, 35.0), omega=0.4)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.int64)
+    models, info = ref.stream(fr_x, fr_y, ts.astype(np.uint64), config=0, scale=3, max_iter=-1, stm_disable=False)
+    assert len(models) >= 15
+    seeded, free = _chain_case(fr_x, fr_y, ts, list(models), info.tolist(), -1, ctx240)
+    knife = []
+    for k in np.nonzero(seeded >= 1e-4)[0]:
+        idx, start = ring_slice(ts, info[k][0])
+        rev = idx[::-1]
+        t_rev = (ts[rev] - start).astype(np.int32)
+        r = oracle_port.minimize(fr_x[rev], fr_y[rev], t_rev, scale=3, max_iter=-1, init_model=models[k - 1] if k else None, accum_mode=0)
+        own = np.max(np.abs(r["model"][7:9] - models[k][7:9]) / np.abs(models[k][7:9]))
+        assert own > 2.5e-5, (k, seeded[k], own)
+        knife.append((int(k), float(seeded[k]), float(own)))
+    assert len(knife) <= len(models) // 10, knife
+    out = {"slices": len(models), "seeded_max_rel": float(seeded.max()), "free_running_max_rel": float(free.max()),
+           "knife_edge_slices": knife, "seeded": [float(v) for v in seeded], "free_running": [float(v) for v in free]}
+    print("reference warm-start chain:", out)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "chain_deviation.json"), "w") as f:
+        import json
+        json.dump(out, f)

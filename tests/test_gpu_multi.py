@@ -60,6 +60,36 @@ def test_multi_equals_single_context(ctx240, n_dev):
         m.close()
 
 
+def test_multi_large_sensor_needs_more_than_48k_shared_memory_on_every_device():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per device: a 1280x720 context at scale 3 needs ~60 KB of
+    dynamic shared memory, so every device of a bf_multi front must have had the attribute raised (round 1 raised
+    it on device 0 only and the launch on devices 1.. failed with 'invalid argument')."""
+    n_dev = min(2, bf.load().bf_device_count())
+    st = synth.make_stream(1280, 720, 20e6, 0.02, seed=67)
+    sls = synth.cut_slices(st, 0.0025)[:8]
+    one = bf.Context(720, 1280, 3, max_events=len(st) + 16, max_slices=9, device=0)
+    try:
+        assert one.get_option("smem_bytes") > 48 * 1024
+        for s in sls:
+            one.add(s.fr_x, s.fr_y, s.t_ns, 3, 3)
+        one.run()
+        want = one.results()
+    finally:
+        one.close()
+    m = bf.MultiContext(n_dev, 720, 1280, 3, max_events_per_device=len(st) + 16, max_slices_per_device=9)
+    try:
+        m.set_option("block", 1)                 # slices alternate between the devices
+        for s in sls:
+            m.add_packed(bf.pack_events(s.fr_x, s.fr_y, s.t_ns), 3, 3)
+        m.run()
+        m.sync()
+        same_results(m.results(), want)
+        if n_dev > 1:
+            assert sorted(set(m.locate(k)[1] for k in range(len(sls)))) == [0, 1]
+    finally:
+        m.close()
+
+
 def test_multi_ragged_batches(ctx240):
     """Fewer slices than devices x block, an empty batch, and a slice below the 1000-event guard."""
     n_dev = min(2, bf.load().bf_device_count())

@@ -254,6 +254,45 @@ def test_streamed_upload_equals_plain_run():
         c.close()
 
 
+def test_streamed_upload_of_alternating_batches():
+    """Back-to-back streamed runs of DIFFERENT batches (ping-pong device buffers, the H2D of batch k+1 under the
+    kernel of batch k, many small upload chunks, slice boundaries that are not 32-byte aligned): every batch must
+    give the records of a plain run of the same batch.  Covers the hazard of an L1-cached sector that straddles two
+    slices and was read before the second slice had landed (events are loaded L2-coherent)."""
+    import better_flow_b200 as bf
+    batches = []
+    for seed in (92, 93):
+        st = synth.make_stream(240, 180, 3e6, 0.3, seed=seed)
+        sls = synth.cut_slices(st, 0.005)
+        sls = [synth.Slice(s.fr_x[:len(s.fr_x) - (k % 4)], s.fr_y[:len(s.fr_y) - (k % 4)], s.t_ns[:len(s.t_ns) - (k % 4)], s.rows, s.cols)
+               for k, s in enumerate(sls)]            # odd lengths: slices start at every residue of 4 events
+        batches.append(sls)
+    cap = max(sum(len(s.fr_x) for s in b) for b in batches)
+    c = bf.Context(180, 240, 3, max_events=cap + 16, max_slices=max(len(b) for b in batches) + 1, device=0)
+    try:
+        want = []
+        for b in batches:
+            c.reset()
+            for s in b:
+                c.add(s.fr_x, s.fr_y, s.t_ns, 3, 4)
+            c.run()
+            want.append([(r["iters"], r["model"].copy()) for r in c.results()])
+        c.set_option("upload_chunks", 60)
+        for rep in range(6):
+            k = rep % 2
+            c.reset()
+            for s in batches[k]:
+                c.add(s.fr_x, s.fr_y, s.t_ns, 3, 4)
+            c.run_streamed()
+            c.sync()                                   # (the staging buffer is rewritten by the next reset / add)
+            got = c.results()
+            assert len(got) == len(want[k])
+            for (it, m), r in zip(want[k], got):
+                assert r["rc"] == 0 and r["iters"] == it and same_model(m, r["model"])
+    finally:
+        c.close()
+
+
 def test_permutation_invariance_bit_exact(ctx240):
     """Integer accumulation makes the result independent of the order of the events -- to the last bit."""
     sl = slices_240(95, 0.03, 1)[0]
