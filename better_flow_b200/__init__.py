@@ -23,6 +23,7 @@ FLAG_ALL_NOISE, FLAG_T_QUANTISED = 1, 2
 EVENT_NOISE = 0x8000
 
 EVENT_DTYPE = np.dtype([("fr_x", "<u2"), ("fr_y", "<u2"), ("t_ns", "<i4")])
+RING_EVENT_DTYPE = np.dtype([("fr_x", "<u2"), ("fr_y", "<u2"), ("reserved", "<u4"), ("timestamp", "<u8")])   # bf_ring_event
 
 
 class Model(C.Structure):
@@ -64,6 +65,7 @@ ABI_SYMBOLS = (
     "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
+    "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed",
 )
 
 _lib = None
@@ -134,6 +136,16 @@ def load() -> C.CDLL:
         lib.bf_multi_locate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.bf_multi_launch_count.argtypes = [C.c_void_p]
         lib.bf_multi_launch_count.restype = C.c_longlong
+        lib.bf_ring_create.restype = C.c_void_p
+        lib.bf_ring_create.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+        lib.bf_ring_destroy.argtypes = [C.c_void_p]
+        lib.bf_ring_destroy.restype = None
+        lib.bf_ring_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.bf_ring_slice.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        lib.bf_ring_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(SliceResult)]
+        lib.bf_ring_sync.argtypes = [C.c_void_p]
+        lib.bf_ring_pushed.argtypes = [C.c_void_p]
+        lib.bf_ring_pushed.restype = C.c_longlong
         assert C.sizeof(SliceResult) == RESULT_BYTES and C.sizeof(Model) == 88
         _lib = lib
     return _lib
@@ -368,6 +380,53 @@ class Context:
         self._chk(self.lib.bf_project(self.h, len(fx), _ptr(fx), _ptr(fy), _ptr(t), _ptr(px), _ptr(py), _ptr(nx),
                                       _ptr(ny), dnx, dny, cx, cy, div, crl))
         return px, py, nx, ny
+
+
+class Ring:
+    """bf_ring: the device-resident slice ring of DVS_flow's default mode (include/bf_cuda.h)."""
+
+    def __init__(self, ctx: "Context", capacity=50000, max_pending=64):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.h = self.lib.bf_ring_create(ctx.h, int(capacity), int(max_pending))
+        if not self.h:
+            raise BfError(self.lib.bf_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bf_ring_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise BfError(self.lib.bf_last_error().decode())
+        return rc
+
+    def push(self, fr_x, fr_y, timestamp_ns):
+        ev = np.zeros(len(fr_x), dtype=RING_EVENT_DTYPE)
+        ev["fr_x"], ev["fr_y"], ev["timestamp"] = fr_x, fr_y, timestamp_ns
+        self._chk(self.lib.bf_ring_push(self.h, _ptr(ev), len(ev)))
+
+    def slice(self, n, slice_start, scale=3, max_iter=-1, chain=True) -> int:
+        return self._chk(self.lib.bf_ring_slice(self.h, int(n), int(slice_start), scale, max_iter, 1 if chain else 0))
+
+    def result(self, ticket) -> dict:
+        r = SliceResult()
+        self._chk(self.lib.bf_ring_result(self.h, int(ticket), C.byref(r)))
+        return _result_dict(r)
+
+    def sync(self):
+        self._chk(self.lib.bf_ring_sync(self.h))
+
+    @property
+    def pushed(self):
+        return int(self.lib.bf_ring_pushed(self.h))
 
 
 def _result_dict(r: SliceResult) -> dict:

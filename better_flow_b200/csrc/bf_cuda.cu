@@ -35,6 +35,10 @@ struct __align__(16) Smem {
     int cont;
     int guard;
     int minmax[6];
+#if BF_TMA_PATCH
+    unsigned long long tma_bar[BF_NW];     // one mbarrier per warp (TMA tile staging of the cell patches)
+    unsigned tma_phase[BF_NW];
+#endif
 };
 
 __device__ __forceinline__ void copy_cg(void *dst, const void *src, int bytes);
@@ -51,7 +55,7 @@ struct LoopState {
 };
 
 template <int SH>
-__device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
+__device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMaps *tm) {
     GroupWs *ws = P.ws + L.vgroup;
     u64 *img0 = P.images + (size_t)L.vgroup * 2 * P.img_elems;
     u64 *img1 = img0 + P.img_elems;
@@ -101,9 +105,26 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
 
         Acc acc;
         acc_zero(acc);
+#if BF_TMA_PATCH
+        {
+            const int warp = threadIdx.x >> 5;
+            TmaWarp tw;
+            tw.map = &tm->m[SH];
+            tw.buf = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(&S) + P.tma_off) + (size_t)warp * P.tma_tile_elems;
+            tw.bar = smem_u32(&S.tma_bar[warp]);
+            tw.phase = S.tma_phase[warp];
+            tw.img_index = L.vgroup * 2 + buf;
+            n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, G, S.list[buf], S.scan,
+                                           nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
+                                           n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev, &tw);
+            if ((threadIdx.x & 31) == 0) S.tma_phase[warp] = tw.phase;
+        }
+#else
+        (void)tm;
         n_prev = image_pass<SH, false>(acc, img_new, P.pitch, S.g, S.pk, S.rcp_tab, flags_new, tag, rank, G, S.list[buf], S.scan,
                                        nullptr, nullptr, nullptr, iter > 0 ? img_old : nullptr, flags_old, tag - 1,
                                        n_prev >= 0 ? S.list[buf ^ 1] : nullptr, n_prev);
+#endif
         if (pf) __syncthreads();
         PF_MARK(PF_CELLS);
         acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
@@ -177,7 +198,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L) {
 // OptimizerRolling::run for the slice in S.sd, owned by this CTA's group.
 template <int SH>
 __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
-                          int rank) {
+                          int rank, const TmaMaps *tm) {
     if (threadIdx.x == 0) {
         bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
         if (S.sd.has_init) {
@@ -194,7 +215,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     LoopState L;
     L.vgroup = group; L.rank = rank; L.G = P.G; L.iter = 0; L.buf = 0; L.n_prev = -1;
     L.tag = tag; L.bar_target = bar_target; L.helper = false;
-    slice_loop<SH>(P, S, L);
+    slice_loop<SH>(P, S, L, tm);
     tag = L.tag; bar_target = L.bar_target;
     // the slice is over: nobody can join any more (a helper that had claimed but not joined sees 0 and leaves)
     if (P.allow_help && rank == 0 && threadIdx.x == 0) atomicExch(&ws->help_state, (unsigned)HELP_CLOSED);
@@ -202,7 +223,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
 
 // HELPING, helper side: join the slice group `v` is minimising (its leader has published P.join[v]).
 template <int SH>
-__device__ void help_slice(const KParams &P, Smem &S, int v, int my_rank) {
+__device__ void help_slice(const KParams &P, Smem &S, int v, int my_rank, const TmaMaps *tm) {
     const JoinRecord &r = P.join[v];
     if (threadIdx.x == 0) {
         copy_cg(&S.sd, &r.sd, (int)sizeof(SliceDesc));
@@ -216,13 +237,13 @@ __device__ void help_slice(const KParams &P, Smem &S, int v, int my_rank) {
     L.vgroup = v; L.rank = __ldcg(&r.rank_base) + my_rank; L.G = __ldcg(&r.G_new);
     L.iter = __ldcg(&r.iter_next); L.buf = __ldcg(&r.buf); L.n_prev = -1;
     L.tag = __ldcg(&r.tag); L.bar_target = __ldcg(&r.bar_target); L.helper = true;
-    slice_loop<SH>(P, S, L);   // (its leading __syncthreads publishes the shared-memory copy to the CTA)
+    slice_loop<SH>(P, S, L, tm);   // (its leading __syncthreads publishes the shared-memory copy to the CTA)
 }
 
 // OptimizerLocal::run (optimizer_sampler.cpp:4-38) for the slice in S.sd: same double-buffered
 // event pass -> barrier -> image pass -> barrier -> control step cycle as run_slice, one cycle per
 // iteration_step.
-__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank);
+__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank, const TmaMaps *tm);
 
 template <int SH>
 __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
@@ -293,7 +314,7 @@ __device__ __forceinline__ void copy_cg(void *dst, const void *src, int bytes) {
 }
 
 // HELPING, helper side (see bf_device.cuh).  Entered by a group that found the slice queue empty.
-__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank) {
+__device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, int group, int rank, const TmaMaps *tm) {
     const int n_groups = (int)gridDim.x / P.G;
     if (rank == 0 && threadIdx.x == 0) atomicAdd(P.groups_done, 1u);
     for (;;) {
@@ -344,9 +365,9 @@ __device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar
         if (joined) {
             const int scale = __ldcg(&P.join[v].sd.scale);
             switch (scale) {
-                case 1: help_slice<0>(P, S, v, rank); break;
-                case 3: help_slice<1>(P, S, v, rank); break;
-                default: help_slice<2>(P, S, v, rank); break;
+                case 1: help_slice<0>(P, S, v, rank, tm); break;
+                case 3: help_slice<1>(P, S, v, rank, tm); break;
+                default: help_slice<2>(P, S, v, rank, tm); break;
             }
         }
         __syncthreads();
@@ -356,8 +377,8 @@ __device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar
 // MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
 // (twice the warps to hide L2 latency, at the price of a few spills).
 template <int MINB>
-__global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams P, const __grid_constant__ TmaMaps TM) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int group = blockIdx.x / P.G;
     const int rank = blockIdx.x - group * P.G;
@@ -368,6 +389,13 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
     long long *pf = P.prof ? P.prof + (size_t)blockIdx.x * BF_NPROF : nullptr;
     const long long t_begin = pf ? clock64() : 0;
     fill_rcp_table(S.rcp_tab);   // made visible by the first group barrier's __syncthreads
+#if BF_TMA_PATCH
+    if (threadIdx.x < BF_NW) {
+        mbar_init(smem_u32(&S.tma_bar[threadIdx.x]), 1u);
+        S.tma_phase[threadIdx.x] = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     if (P.bm_words > 0) {
         unsigned *bm = reinterpret_cast<unsigned *>(smem_raw + sizeof(Smem) + (size_t)P.tab_rows * sizeof(int2) +
                                                     (size_t)P.tab_cols * sizeof(short2));
@@ -393,11 +421,18 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
         const int slice = __ldcg(&ws->cur_slice);
         if (slice >= P.n_slices) {
             if (!P.allow_help) break;
-            help_phase(P, S, ws, bar_target, group, rank);   // HELPING, helper side: returns when nothing is left to help
+            help_phase(P, S, ws, bar_target, group, rank, &TM);   // HELPING, helper side: returns when nothing is left to help
             break;
         }
         if (threadIdx.x == 0) {
             S.sd = P.slices[slice];
+            if (S.sd.has_init == 2) {
+                // warm start from the PREVIOUS slice's result record, which is still on the device (bf_ring_slice:
+                // set_model(last_model), dvs_flow.h:218-219, without a host round trip); the launch that wrote it
+                // precedes this one in stream order
+                copy_cg(&S.sd.init, &P.chain_src->model, (int)sizeof(bf_model));
+                S.sd.has_init = 1;
+            }
             S.minmax[0] = INT_MAX; S.minmax[1] = INT_MIN; S.minmax[2] = INT_MAX;
             S.minmax[3] = INT_MIN; S.minmax[4] = INT_MAX; S.minmax[5] = INT_MIN;
         }
@@ -465,9 +500,9 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             else run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
         } else if (guard == 0) {
             switch (S.sd.scale) {
-                case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank); break;
-                case 3: run_slice<1>(P, S, ws, bar_target, tag, group, rank); break;
-                default: run_slice<2>(P, S, ws, bar_target, tag, group, rank); break;
+                case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank, &TM); break;
+                case 3: run_slice<1>(P, S, ws, bar_target, tag, group, rank, &TM); break;
+                default: run_slice<2>(P, S, ws, bar_target, tag, group, rank, &TM); break;
             }
         } else if (threadIdx.x == 0) {
             bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
@@ -548,7 +583,7 @@ __global__ void bf_stage_splat_kernel(const StageParams P, int clear) {
 
 template <int SH>
 __global__ void __launch_bounds__(BF_NT, 1) bf_stage_image_kernel(const StageParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     Acc acc;
     acc_zero(acc);
@@ -644,6 +679,40 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
     }
 }
 
+// ---- device-resident slice ring (include/bf_cuda.h: bf_ring_*) -------------------------------------------------
+// Cuts "the newest n events, newest -> oldest, local time = timestamp - start" (what a range-for over the
+// reference's CircularArray hands to the optimiser, dvs_flow.h:196-198 + Event::set_local_time, event.h:61-63) out of
+// the ring into the packed event buffer, and writes the slice descriptor.  Event g of the stream lives at ring index
+// g % cap.  If the previous slice hit the tiny-window guard, its events (stream indices [prev_lo, prev_hi)) are marked
+// as noise here -- in the ring too -- exactly as run() marks them in the reference's buffer (optimizer_rolling.h:49-55).
+__global__ void bf_ring_build_kernel(bf_ring_event *ring, long long cap, long long head, int n, unsigned long long start,
+                                     bf_event *out, SliceDesc *desc, int scale, int max_iter, int chain,
+                                     const bf_slice_result *prev, long long prev_lo, long long prev_hi) {
+    const bool prev_noise = prev != nullptr && (prev->flags & BF_FLAG_ALL_NOISE) != 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long g = head - 1 - i;
+        bf_ring_event *slot = ring + (g % cap);
+        const bf_ring_event e = *slot;
+        unsigned fy = e.fr_y;
+        if (prev_noise && g >= prev_lo && g < prev_hi && !(fy & BF_EVENT_NOISE)) {
+            fy |= BF_EVENT_NOISE;
+            slot->fr_y = (uint16_t)fy;
+        }
+        long long dt = (long long)(e.timestamp - start);
+        dt = dt > (long long)INT_MAX ? (long long)INT_MAX : (dt < (long long)INT_MIN ? (long long)INT_MIN : dt);   // (the host checks the range)
+        bf_event o;
+        o.fr_x = e.fr_x; o.fr_y = (uint16_t)fy; o.t_ns = (int32_t)dt;
+        out[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        SliceDesc d;
+        d.ev_off = 0; d.n = n; d.scale = scale; d.max_iter = max_iter; d.has_init = chain ? 2 : 0; d.mode = 0; d.pad_ = 0;
+        d.init.cx = d.init.cy = d.init.dx = d.init.dy = d.init.rot = d.init.div = 0; d.init.cnt = 0; d.init.pad_ = 0;
+        d.init.total_dx = d.init.total_dy = d.init.total_rot = d.init.total_div = 0;
+        *desc = d;
+    }
+}
+
 // =================================================================================================
 // Host side
 // =================================================================================================
@@ -695,7 +764,10 @@ struct bf_ctx {
 
     // options
     int opt_group = 0;          // CTAs per slice; 0 = auto (from the batch size)
-    int min_group = 2;          // smallest automatic group (measured: 2 >= 3 > 4 > 6 > 1 on DAVIS-240C)
+    int min_group = 4;          // smallest automatic group.  DAVIS-240C, 592 slices, ms per launch (profiles/r2c_ab_group_size.txt):
+                                // G = 2: 13.55, 3: 13.26, 4: 13.27, 5: 13.7, 6: 14.1, 8: 14.9, 16: 18.8 -- fewer slices in flight raise the
+                                // L2 hit rate (35 -> 39 -> 72 % at G = 2, 4, 16) but every iteration pays its barriers and its serial GD
+                                // step over less work per CTA; 4 also halves the image allocation of G = 2
     int ctas_per_sm = 2;        // 1 or 2 resident CTAs per SM
     long long image_budget_mb = 24576;   // cap on the point-image allocation
     int n_groups_alloc = 0;
@@ -731,11 +803,14 @@ struct bf_ctx {
     unsigned *d_flags = nullptr;
     long long flag_elems = 0;
     unsigned launch_seq = 0;     // tag_base = launch_seq << 20; flags are re-zeroed when it wraps
+    TmaMaps tmaps;               // BF_TMA_PATCH: tensor maps over d_images, one per scale (re-encoded when the images are re-allocated)
     long long *d_prof = nullptr; // debug phase counters
     int profile = 0;
     // stage scratch
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
+
+    std::vector<struct bf_ring *> rings;   // device-resident slice rings of this context (destroyed with it)
 
     // batch state
     int n_slices = 0;
@@ -746,11 +821,21 @@ struct bf_ctx {
 
 static size_t smem_bytes() { return sizeof(Smem); }
 // per-CTA stamp bitmap: one bit per cell flag (flag_elems is a multiple of 64)
-static int bm_words_of(const bf_ctx *c) { return (int)(c->flag_elems / 32); }
+static int bm_words_of(const bf_ctx *c) { return (int)(BF_STAMP_BYTES ? c->flag_elems / 4 : c->flag_elems / 32); }
 // minimise kernel: fixed block + the per-slice cell tables (int2 per image row, short2 per image column)
-static size_t smem_bytes_min(const bf_ctx *c) {
+static size_t smem_tables_end(const bf_ctx *c) {
     return sizeof(Smem) + (size_t)c->max_scale * c->res_x * sizeof(int2) + (size_t)c->max_scale * c->res_y * sizeof(short2) +
            (size_t)bm_words_of(c) * sizeof(unsigned);
+}
+// BF_TMA_PATCH: one (8 + 2H) x 32 tile of packed words per warp behind the tables, 128-byte aligned
+static int tma_tile_elems_of(const bf_ctx *c) { return (BF_CELL_ROWS + 2 * (c->max_scale / 2 + 1)) * 32; }
+static size_t tma_off_of(const bf_ctx *c) { return (smem_tables_end(c) + 127) & ~(size_t)127; }
+static size_t smem_bytes_min(const bf_ctx *c) {
+#if BF_TMA_PATCH
+    return tma_off_of(c) + (size_t)BF_NW * tma_tile_elems_of(c) * sizeof(u64);
+#else
+    return smem_tables_end(c);
+#endif
 }
 
 static int ensure_device() {
@@ -782,7 +867,7 @@ static int max_groups(bf_ctx *c) {
     return g;
 }
 
-static void pick_launch(bf_ctx *c, int n_slices, int *G, int *n_groups) {
+static void pick_launch(bf_ctx *c, int n_slices, long long n_events, int *G, int *n_groups) {
     const int slots = c->sms * c->ctas_per_sm;
     int groups = c->n_groups_alloc;
     if (c->opt_group <= 0) groups = std::min(groups, std::max(1, n_slices));
@@ -793,7 +878,7 @@ static void pick_launch(bf_ctx *c, int n_slices, int *G, int *n_groups) {
         // a group and one record per CTA in the reduction, so beyond ~3000 events per CTA more CTAs make a
         // slice slower (single DAVIS-240C slice: 0.247 ms at G = 16..32, 0.299 ms at G = 296; measured sweep
         // in tools/sweep_single.py).
-        const long long per_slice = c->n_events / std::max(1, n_slices);
+        const long long per_slice = n_events / std::max(1, n_slices);
         const int cap = (int)std::min<long long>(slots, std::max<long long>(16, per_slice / 3000));
         g = std::max(std::min(g, cap), std::min(c->min_group, g));
     }
@@ -817,7 +902,8 @@ static int next_tag_base(bf_ctx *c, unsigned *tag_base) {
     return BF_OK;
 }
 
-static int configure(bf_ctx *c, int n_slices) {
+static int configure(bf_ctx *c, int n_slices, long long n_events = -1) {
+    if (n_events < 0) n_events = c->n_events;
     const int want = max_groups(c);
     if (want != c->n_groups_alloc || !c->d_images) {
         CU(cudaStreamSynchronize(c->stream));
@@ -840,8 +926,30 @@ static int configure(bf_ctx *c, int n_slices) {
         // one record per CTA slot, times BF_MAX_GROW: a helped slice is worked on by up to BF_MAX_GROW groups
         CU(cudaMalloc(&c->d_partials, (size_t)c->sms * 4 * BF_MAX_GROW * BF_NSUMS * sizeof(double)));
         CU(cudaMalloc(&c->d_join, (size_t)want * sizeof(JoinRecord)));
+#if BF_TMA_PATCH
+        {
+            // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+            typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                          const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) return fail(BF_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+            const cuuint64_t dims[3] = {(cuuint64_t)c->pitch, (cuuint64_t)c->rows_alloc, (cuuint64_t)want * 2};
+            const cuuint64_t strides[2] = {(cuuint64_t)c->pitch * sizeof(u64), (cuuint64_t)c->img_elems * sizeof(u64)};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            for (int k = 0; k < 3; ++k) {
+                const cuuint32_t box[3] = {32u, (cuuint32_t)(BF_CELL_ROWS + 2 * (k + 1)), 1u};
+                const CUresult r = ((encode_fn)fn)(&c->tmaps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, c->d_images, dims, strides, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(BF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+            }
+        }
+#endif
     }
-    pick_launch(c, n_slices, &c->G, &c->n_groups);
+    pick_launch(c, n_slices, n_events, &c->G, &c->n_groups);
     return BF_OK;
 }
 
@@ -922,7 +1030,7 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
     c->ev_buf[0] = c->d_events; c->sl_buf[0] = c->d_slices;
     if ((e = cudaMalloc(&c->d_results, (size_t)max_slices * sizeof(bf_slice_result))) != cudaSuccess) return bail("cudaMalloc(results)", e);
 
-    if (smem_bytes_min(c) > 100 * 1024) {
+    if (smem_bytes_min(c) > 112 * 1024) {
         fail(BF_ERR_ARG, "sensor too large for the per-slice cell tables (%zu bytes of shared memory)", smem_bytes_min(c));
         bf_ctx_destroy(c);
         return nullptr;
@@ -949,6 +1057,7 @@ void bf_ctx_destroy(bf_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    while (!c->rings.empty()) bf_ring_destroy(c->rings.back());   // (each removes itself from the list)
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
     cudaFree(c->ev_buf[0]); cudaFree(c->ev_buf[1]); cudaFree(c->sl_buf[0]); cudaFree(c->sl_buf[1]);
     cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy);
@@ -1181,28 +1290,41 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     return bf_batch_download(c);
 }
 
-static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
+// One persistent launch over `n_slices` slice descriptors.
+struct LaunchSpec {
+    const bf_event *events;
+    const SliceDesc *slices;          // device
+    bf_slice_result *results;         // device, [n_slices]
+    int n_slices;
+    long long n_events;               // (launch geometry only)
+    const unsigned *ready;
+    const bf_slice_result *chain_src; // device record for slices with has_init == 2, or null
+    int want_events;
+};
+
+static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
     CU(cudaSetDevice(c->device));
-    if (c->n_slices == 0) { c->ran = true; return BF_OK; }
-    int rc = configure(c, c->n_slices);
+    int rc = configure(c, L.n_slices, L.n_events);
     if (rc != BF_OK) return rc;
-    if (want_events && !c->d_nxy) {
+    if (L.want_events && !c->d_nxy) {
         CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
         CU(cudaMalloc(&c->d_pr_out, (size_t)c->max_events * sizeof(double2)));
     }
     CU(cudaMemsetAsync(c->d_ctrl, 0, c->ctrl_bytes, c->stream));
     KParams P;
-    P.events = c->d_events; P.state = c->d_state;
-    P.nxy = want_events ? c->d_nxy : nullptr; P.pr_out = want_events ? c->d_pr_out : nullptr;
-    P.slices = c->d_slices; P.results = c->d_results; P.n_slices = c->n_slices;
+    P.events = L.events; P.state = c->d_state;
+    P.nxy = L.want_events ? c->d_nxy : nullptr; P.pr_out = L.want_events ? c->d_pr_out : nullptr;
+    P.slices = L.slices; P.results = L.results; P.n_slices = L.n_slices;
     P.queue = reinterpret_cast<int *>(c->d_ctrl);
     P.ws = reinterpret_cast<GroupWs *>(c->d_ctrl + 256);
     P.partials = c->d_partials; P.images = c->d_images; P.img_elems = c->img_elems; P.pitch = c->pitch;
     P.flags = c->d_flags; P.flag_elems = c->flag_elems;
     if ((rc = next_tag_base(c, &P.tag_base)) != BF_OK) return rc;
     P.G = c->G; P.res_x = c->res_x; P.res_y = c->res_y; P.min_events = c->min_events;
-    P.iter_cap = c->iter_cap; P.want_events = want_events ? 1 : 0;
-    P.ready = ready;
+    P.iter_cap = c->iter_cap; P.want_events = L.want_events ? 1 : 0;
+    P.ready = L.ready;
+    P.chain_src = L.chain_src;
+    P.tma_off = (int)tma_off_of(c); P.tma_tile_elems = tma_tile_elems_of(c);
     P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
     P.bm_words = bm_words_of(c);
     P.allow_help = (c->tail_help && c->n_groups > 1) ? 1 : 0;
@@ -1210,7 +1332,7 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     if (c->opt_group <= 0) {
         // a slice stops profiting from more CTAs at ~800 events per CTA (but take at least 64): measured sweep,
         // profiles/r1f_single_slice_sweep.txt
-        const long long per_slice = c->n_events / std::max(1, c->n_slices);
+        const long long per_slice = L.n_events / std::max(1, L.n_slices);
         const long long want_ctas = std::max<long long>(64, per_slice / 800);
         P.max_grow = (int)std::max<long long>(1, std::min<long long>(P.max_grow, (want_ctas + c->G - 1) / c->G));
     }
@@ -1223,7 +1345,7 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
         CU(cudaMemsetAsync(c->d_prof, 0, (size_t)1024 * BF_NPROF * sizeof(long long), c->stream));
         P.prof = c->d_prof;
     }
-    void *args[] = {&P};
+    void *args[] = {&P, &c->tmaps};
     void *kern = c->ctas_per_sm == 2 ? (void *)bf_minimize_kernel<2> : (void *)bf_minimize_kernel<1>;
 #if BF_NT <= 256
     if (c->ctas_per_sm == 4) kern = (void *)bf_minimize_kernel<4>;
@@ -1231,6 +1353,15 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
     CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
     CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this)
     c->launches += 1;
+    return BF_OK;
+}
+
+static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
+    CU(cudaSetDevice(c->device));
+    if (c->n_slices == 0) { c->ran = true; return BF_OK; }
+    LaunchSpec L{c->d_events, c->d_slices, c->d_results, c->n_slices, c->n_events, ready, nullptr, want_events};
+    const int rc = launch_spec(c, L);
+    if (rc != BF_OK) return rc;
     c->ran = true;
     c->have_events = want_events != 0;
     return BF_OK;
@@ -1474,6 +1605,138 @@ int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, con
     if (nx) CU(cudaMemcpyAsync(nx, base + o_nx, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (ny) CU(cudaMemcpyAsync(ny, base + o_ny, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+// ---- device-resident slice ring ------------------------------------------------------------------------------
+struct bf_ring {
+    bf_ctx *c = nullptr;
+    long long cap = 0;
+    int max_pending = 0;
+    bf_ring_event *d_ring = nullptr;
+    bf_ring_event *h_stage = nullptr;   // pinned staging ring, `stage_cap` entries
+    long long stage_cap = 0, stage_pos = 0;
+    struct Push { cudaEvent_t ev; long long lo, hi; bool open; };
+    std::vector<Push> pushes;           // the last copies issued from the staging ring
+    size_t push_next = 0;
+    long long pushed = 0;
+    SliceDesc *d_desc = nullptr;        // [max_pending]
+    bf_slice_result *d_res = nullptr;   // [max_pending + 1]: slot max_pending is the all-zero record (last_model of a fresh DVS_flow)
+    bf_slice_result *h_res = nullptr;   // pinned [max_pending]
+    std::vector<cudaEvent_t> done;
+    int next_ticket = 0;
+    int prev_slot = -1;
+    long long prev_lo = 0, prev_hi = 0;
+};
+
+bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
+    if (!c || capacity <= 0 || capacity + 2 > c->max_events || max_pending < 2) {
+        fail(BF_ERR_ARG, "bf_ring_create: capacity must be positive and below the context's max_events, max_pending >= 2");
+        return nullptr;
+    }
+    if (cudaSetDevice(c->device) != cudaSuccess) { fail(BF_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    bf_ring *r = new bf_ring();
+    r->c = c; r->cap = capacity; r->max_pending = max_pending;
+    r->stage_cap = std::max<long long>(2 * capacity, 1 << 18);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return x == cudaSuccess; };
+    ok(cudaMalloc(&r->d_ring, (size_t)capacity * sizeof(bf_ring_event)));
+    ok(cudaMemset(r->d_ring, 0, (size_t)capacity * sizeof(bf_ring_event)));
+    ok(cudaMallocHost(&r->h_stage, (size_t)r->stage_cap * sizeof(bf_ring_event)));
+    ok(cudaMalloc(&r->d_desc, (size_t)max_pending * sizeof(SliceDesc)));
+    ok(cudaMalloc(&r->d_res, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
+    ok(cudaMemset(r->d_res, 0, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
+    ok(cudaMallocHost(&r->h_res, (size_t)max_pending * sizeof(bf_slice_result)));
+    r->done.resize((size_t)max_pending, nullptr);
+    for (auto &ev : r->done) ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    r->pushes.resize(16);
+    for (auto &p : r->pushes) { p.ev = nullptr; p.lo = p.hi = 0; p.open = false; ok(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming)); }
+    if (e != cudaSuccess) {
+        fail(BF_ERR_CUDA, "bf_ring_create failed: %s", cudaGetErrorString(e));
+        bf_ring_destroy(r);
+        return nullptr;
+    }
+    c->rings.push_back(r);
+    return r;
+}
+
+void bf_ring_destroy(bf_ring *r) {
+    if (!r) return;
+    cudaSetDevice(r->c->device);
+    cudaStreamSynchronize(r->c->stream);
+    r->c->rings.erase(std::remove(r->c->rings.begin(), r->c->rings.end(), r), r->c->rings.end());
+    cudaFree(r->d_ring); cudaFreeHost(r->h_stage); cudaFree(r->d_desc); cudaFree(r->d_res); cudaFreeHost(r->h_res);
+    for (auto ev : r->done) if (ev) cudaEventDestroy(ev);
+    for (auto &p : r->pushes) if (p.ev) cudaEventDestroy(p.ev);
+    delete r;
+}
+
+long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
+
+int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
+    if (!r || n < 0 || (n > 0 && !ev)) return fail(BF_ERR_ARG, "bf_ring_push: bad arguments");
+    bf_ctx *c = r->c;
+    CU(cudaSetDevice(c->device));
+    if (n > r->cap) { ev += n - r->cap; r->pushed += n - r->cap; n = (int)r->cap; }   // only the newest `cap` can ever be used
+    unsigned bad = 0;
+    for (int i = 0; i < n; ++i) bad |= (unsigned)((int)ev[i].fr_x >= c->res_x) | (unsigned)((int)(ev[i].fr_y & 0x7fffu) >= c->res_y);
+    if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
+    int done_n = 0;
+    while (done_n < n) {
+        // one piece = contiguous both in the staging ring and in the device ring
+        const long long s_off = r->stage_pos % r->stage_cap, d_off = r->pushed % r->cap;
+        const int piece = (int)std::min<long long>(std::min<long long>(n - done_n, r->stage_cap - s_off), r->cap - d_off);
+        // the staging entries must not be rewritten while an earlier copy may still be reading them
+        for (auto &p : r->pushes)
+            if (p.open && p.lo < s_off + piece && s_off < p.hi) { CU(cudaEventSynchronize(p.ev)); p.open = false; }
+        memcpy(r->h_stage + s_off, ev + done_n, (size_t)piece * sizeof(bf_ring_event));
+        CU(cudaMemcpyAsync(r->d_ring + d_off, r->h_stage + s_off, (size_t)piece * sizeof(bf_ring_event), cudaMemcpyHostToDevice, c->stream));
+        bf_ring::Push &p = r->pushes[r->push_next++ % r->pushes.size()];
+        if (p.open) CU(cudaEventSynchronize(p.ev));
+        p.lo = s_off; p.hi = s_off + piece; p.open = true;
+        CU(cudaEventRecord(p.ev, c->stream));
+        r->stage_pos += piece; r->pushed += piece; done_n += piece;
+    }
+    return BF_OK;
+}
+
+int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain) {
+    if (!r || n < 0 || n > r->cap || n > r->pushed) return fail(BF_ERR_ARG, "bf_ring_slice: n exceeds the ring's content");
+    bf_ctx *c = r->c;
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported (1, 3 or 5)", scale);
+    if (scale > c->max_scale) return fail(BF_ERR_ARG, "scale %d exceeds the context's max_scale %d", scale, c->max_scale);
+    CU(cudaSetDevice(c->device));
+    const int ticket = r->next_ticket++;
+    const int slot = ticket % r->max_pending;
+    const bf_slice_result *prev = r->prev_slot >= 0 ? r->d_res + r->prev_slot : r->d_res + r->max_pending;
+    c->uploaded = c->ran = false;                    // the batch entry points' device copy of the events is overwritten
+    const int threads = 256, blocks = std::max(1, std::min(4 * c->sms, (n + threads - 1) / threads));
+    bf_ring_build_kernel<<<blocks, threads, 0, c->stream>>>(r->d_ring, r->cap, r->pushed, n, (unsigned long long)slice_start, c->d_events,
+                                                            r->d_desc + slot, scale, max_iter, chain ? 1 : 0,
+                                                            r->prev_slot >= 0 ? prev : nullptr, r->prev_lo, r->prev_hi);
+    CU(cudaGetLastError());
+    c->launches += 1;
+    LaunchSpec L{c->d_events, r->d_desc + slot, r->d_res + slot, 1, (long long)n, nullptr, prev, 0};
+    const int rc = launch_spec(c, L);
+    if (rc != BF_OK) return rc;
+    CU(cudaMemcpyAsync(r->h_res + slot, r->d_res + slot, sizeof(bf_slice_result), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(r->done[(size_t)slot], c->stream));
+    r->prev_slot = slot; r->prev_lo = r->pushed - n; r->prev_hi = r->pushed;
+    return ticket;
+}
+
+int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out) {
+    if (!r || !out || ticket < 0 || ticket >= r->next_ticket || ticket < r->next_ticket - r->max_pending)
+        return fail(BF_ERR_ARG, "bf_ring_result: ticket %d is not (or no longer) available", ticket);
+    const int slot = ticket % r->max_pending;
+    CU(cudaEventSynchronize(r->done[(size_t)slot]));
+    *out = r->h_res[slot];
+    return BF_OK;
+}
+
+int bf_ring_sync(bf_ring *r) {
+    if (!r) return fail(BF_ERR_ARG, "null ring");
+    CU(cudaStreamSynchronize(r->c->stream));
     return BF_OK;
 }
 

@@ -22,6 +22,7 @@
 // Reference paths are relative to /root/reference/better_flow_core/.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -140,6 +141,9 @@ struct KParams {
     JoinRecord *join;        // [n_groups]
     unsigned *groups_done;   // groups that found the slice queue empty
     const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)
+    const bf_slice_result *chain_src;   // optional: record whose model warm-starts a slice with has_init == 2 (bf_ring_slice)
+    int tma_off;             // BF_TMA_PATCH: byte offset of the per-warp tile buffers in dynamic shared memory (128-byte aligned)
+    int tma_tile_elems;      //               u64 elements per warp buffer
     long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
 };
 #define BF_NPROF 16
@@ -223,6 +227,15 @@ __device__ __forceinline__ uint2 ld_nc_u32x2(const void *p) {   // (one event; s
     return v;
 }
 
+// INVARIANT of the relaxed protocol below: every load of data that ANOTHER CTA wrote during this launch must bypass
+// L1 -- ld.cg / ld.relaxed.gpu (cell flags, image patches, partial sums, bbox, slice ids, join records: __ldcg,
+// ld_relaxed_u32, copy_cg) or, for the event buffer under the streamed upload, ld.global.cg (ld_nc_u32x4).  The only
+// L1-cached cross-iteration data is the per-event state, which a thread re-reads after writing it itself; when a group
+// grows (helping) its members invalidate L1 explicitly (slice_loop).  compute-sanitizer's racecheck does not cover
+// global-memory races, so the evidence for this protocol is the BF_STRICT_SYNC validation build (same results).
+#ifndef BF_STRICT_SYNC
+#define BF_STRICT_SYNC 0
+#endif
 // Barrier over the G CTAs of one group (all co-resident: cooperative launch).  `target` is the
 // CTA-local running arrival total; the counter is zeroed by the host before every launch.
 __device__ __forceinline__ long long group_barrier(unsigned *counter, unsigned &target, int G) {
@@ -238,8 +251,16 @@ __device__ __forceinline__ long long group_barrier(unsigned *counter, unsigned &
         // image patches, partial sums, bbox, slice id) is an L2-coherent ld.cg / relaxed.gpu load, the
         // producers drained their writes with MEMBAR.GPU before arriving (red.release), and the other
         // threads of this CTA are ordered behind this poll by the bar.sync below.
+#if BF_STRICT_SYNC
+        // validation build (-DBF_STRICT_SYNC=1, tools/gpu_strict.sh): the formally correct acquire -- the GPU tests
+        // must give the same results with it, which is the evidence that the relaxed protocol above loses nothing
+        while (ld_acquire_u32(counter) < target) {
+        }
+        fence_acq_rel_gpu();
+#else
         while (ld_relaxed_u32(counter) < target) {
         }
+#endif
         spin = clock64() - t0;
     }
     __syncthreads();
@@ -364,10 +385,20 @@ __device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab,
 // a slice's events stamp each live cell ~50 times per iteration, and every stamp used to be a 4-byte global
 // store on its own L2 sector (more L2 write transactions than the splat itself).  The CTA sets bits while it
 // walks its events and writes the tag once per live cell afterwards (flush_stamp_bitmap).
+// BF_STAMP_BYTES: the per-CTA stamp map holds one BYTE per cell and a stamp is a plain byte store (no read, no
+// atomic: every writer stores the same value) instead of test-then-atomicOr on a bit -- 2 instructions per stamp
+// instead of ~6, at 8x the (small) shared-memory footprint.
+#ifndef BF_STAMP_BYTES
+#define BF_STAMP_BYTES 0
+#endif
+#if BF_STAMP_BYTES
+__device__ __forceinline__ void stamp_bit(unsigned *bm, int f) { reinterpret_cast<unsigned char *>(bm)[f] = 1; }
+#else
 __device__ __forceinline__ void stamp_bit(unsigned *bm, int f) {
     const unsigned b = 1u << (f & 31);
     if (!(bm[f >> 5] & b)) atomicOr(bm + (f >> 5), b);
 }
+#endif
 __device__ __forceinline__ void mark_cells_bm(unsigned *bm, int x, int y, const int2 *row_tab, const short2 *col_tab) {
     const int2 r = row_tab[x];
     const short2 c = col_tab[y];
@@ -383,6 +414,18 @@ __device__ __forceinline__ void mark_cells_bm(unsigned *bm, int x, int y, const 
 // CTA-wide: write `tag` to the flag of every cell whose bit is set and leave the bitmap all-zero again.
 __device__ __forceinline__ void flush_stamp_bitmap(unsigned *bm, unsigned *flags, unsigned tag, int n_cells) {
     __syncthreads();
+#if BF_STAMP_BYTES
+    const int words = (n_cells + 3) >> 2;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        const unsigned m = bm[w];
+        if (m == 0u) continue;
+        bm[w] = 0u;
+        if (m & 0x000000ffu) flags[w * 4 + 0] = tag;
+        if (m & 0x0000ff00u) flags[w * 4 + 1] = tag;
+        if (m & 0x00ff0000u) flags[w * 4 + 2] = tag;
+        if (m & 0xff000000u) flags[w * 4 + 3] = tag;
+    }
+#else
     const int words = (n_cells + 31) >> 5;
     for (int w = threadIdx.x; w < words; w += blockDim.x) {
         unsigned m = bm[w];
@@ -394,6 +437,7 @@ __device__ __forceinline__ void flush_stamp_bitmap(unsigned *bm, unsigned *flags
             flags[w * 32 + b] = tag;
         } while (m != 0u);
     }
+#endif
 }
 
 // ---- event pass: clear old pixel, re-project, splat --------------------------------------------
@@ -541,6 +585,52 @@ __device__ __forceinline__ float unpack_avg_fast(const BfPack &pk, const float2 
     return __fdiv_rn(s, (float)cnt);
 }
 
+// ---- TMA tile staging of the cell patches (BF_TMA_PATCH) ----------------------------------------------------------
+// The image pass reads, per live cell, a (8 + 2H) x 32 tile of packed words: with BF_TMA_PATCH the tile is fetched by
+// the TMA unit (cp.async.bulk.tensor.3d -> UTMALDG) into a per-warp shared-memory buffer and completes on a per-warp
+// mbarrier (SYNCS), one cell AHEAD of the arithmetic: while a warp works on cell k out of registers, the tile of its
+// cell k + 1 is already in flight, so the L2 / HBM latency of the patch loads (a quarter of the image pass's stall
+// samples, profiles/r1j_stall_regions.txt) is off the critical path, and the 12 per-lane LDG.64 with their 64-bit
+// address arithmetic become 12 LDS.64 at immediate offsets.  All images of a context form ONE 3-D tensor
+// [image][row][column] (one CUtensorMap per scale: the box height is 8 + 2H).
+#ifndef BF_TMA_PATCH
+#define BF_TMA_PATCH 0
+#endif
+struct TmaMaps {
+    CUtensorMap m[3];          // scale 1, 3, 5
+};
+struct TmaWarp {               // per-warp staging state (registers)
+    const CUtensorMap *map;
+    u64 *buf;                  // this warp's tile buffer in shared memory (128-byte aligned)
+    unsigned bar;              // shared-memory address of this warp's mbarrier
+    unsigned phase;
+    int img_index;             // index of the image in the 3-D tensor
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "BF_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra BF_MBAR_WAIT_%=;\n\t}" ::"r"(bar), "r"(phase) : "memory");
+}
+// lane 0 of a warp: fetch the patch of cell (ci, cj) of image `img_index` into the warp's buffer
+template <int SH>
+__device__ __forceinline__ void tma_issue_patch(const TmaWarp &t, int ci, int cj) {
+    typedef CellCfg<SH> C;
+    const int c0 = cj * C::CW - C::H + BF_BORDER, c1 = ci * BF_CELL_ROWS - C::H + BF_BORDER;
+    mbar_expect_tx(t.bar, (unsigned)(C::PR * 32 * sizeof(u64)));
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(t.buf)), "l"(t.map), "r"(c0), "r"(c1), "r"(t.img_index), "r"(t.bar) : "memory");
+}
+
 // ---- image pass ------------------------------------------------------------------------------------
 struct Acc {
     int cnt;
@@ -564,6 +654,11 @@ __device__ __forceinline__ void acc_zero(Acc &a) {
 //   Scharr (accel_lib.h:594-605) + sums     lanes H..31-H, rows 1..8
 // Integer packed sums commute, so this equals the reference's per-event s x s splat exactly.
 template <int SH, bool MATERIALISE, bool FAST>
+__device__ __forceinline__ void cell_compute(Acc &acc, const u64 (&P)[CellCfg<SH>::PR], const BfPack &pk, const float2 *rcp_tab,
+                                             int ci, int cj, int rows, int cols, int i0, int j0, float *out_img,
+                                             float *out_gx, float *out_gy);
+
+template <int SH, bool MATERIALISE, bool FAST>
 __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, const float2 *rcp_tab,
                                              int ci, int cj, int rows, int cols, int i0, int j0, float *out_img,
                                              float *out_gx, float *out_gy) {
@@ -574,6 +669,16 @@ __device__ __forceinline__ void cell_process(Acc &acc, const u64 *img, int pitch
     u64 P[C::PR];
 #pragma unroll
     for (int r = 0; r < C::PR; ++r) P[r] = __ldcg(p + (long long)r * pitch);
+    cell_compute<SH, MATERIALISE, FAST>(acc, P, pk, rcp_tab, ci, cj, rows, cols, i0, j0, out_img, out_gx, out_gy);
+}
+
+// The arithmetic of one cell on the point patch held in registers (lane l = patch column l).
+template <int SH, bool MATERIALISE, bool FAST>
+__device__ __forceinline__ void cell_compute(Acc &acc, const u64 (&P)[CellCfg<SH>::PR], const BfPack &pk, const float2 *rcp_tab,
+                                             int ci, int cj, int rows, int cols, int i0, int j0, float *out_img,
+                                             float *out_gx, float *out_gy) {
+    typedef CellCfg<SH> C;
+    const int lane = threadIdx.x & 31;
 
     float A[C::AR];
 #pragma unroll
@@ -749,7 +854,7 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
                           const float2 *rcp_tab, const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
                           const unsigned *flags_clear, unsigned tag_clear, const unsigned short *list_prev,
-                          int n_prev) {
+                          int n_prev, TmaWarp *tma = nullptr) {
     typedef CellCfg<SH> C;
     const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
     const int n_cells = n_ci * n_cj;
@@ -786,6 +891,33 @@ __device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, 
                     const int ci = c / n_cj, cj = c - ci * n_cj;
                     local_cell_process<SH>(acc, img, pitch, pk, ci, cj, g.rows, g.cols);
                 }
+#if BF_TMA_PATCH
+            } else if (pk.fast && tma != nullptr) {
+                // TMA-staged patches, one cell ahead (see TmaWarp)
+                const int lane = threadIdx.x & 31;
+                if (k0 < total && lane == 0) {
+                    // (the splats this tile is made of were written through the generic proxy by other CTAs and became
+                    // visible at barrier A; order this thread's async-proxy reads behind that)
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    const int c = base + (int)list[k0];
+                    tma_issue_patch<SH>(*tma, c / n_cj, c % n_cj);
+                }
+                for (int k = k0; k < total; k += n_warps) {
+                    const int c = base + (int)list[k];
+                    const int ci = c / n_cj, cj = c - ci * n_cj;
+                    mbar_wait(tma->bar, tma->phase);
+                    tma->phase ^= 1u;
+                    u64 P[C::PR];
+#pragma unroll
+                    for (int r = 0; r < C::PR; ++r) P[r] = tma->buf[r * 32 + lane];
+                    __syncwarp();   // every lane has its column in registers: the buffer may be refilled
+                    if (k + n_warps < total && lane == 0) {
+                        const int cn = base + (int)list[k + n_warps];
+                        tma_issue_patch<SH>(*tma, cn / n_cj, cn % n_cj);
+                    }
+                    cell_compute<SH, MATERIALISE, true>(acc, P, pk, rcp_tab, ci, cj, g.rows, g.cols, i0, j0, out_img, out_gx, out_gy);
+                }
+#endif
             } else if (pk.fast) {
                 for (int k = k0; k < total; k += n_warps) {
                     const int c = base + (int)list[k];

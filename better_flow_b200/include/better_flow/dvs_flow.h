@@ -12,12 +12,18 @@
 //   * set_optimizer_local(): minimise every slice with OptimizerLocal (contrast-driven nx, ny descent)
 //     instead of OptimizerRolling; the slice's model then carries total_dx = -nx, total_dy = -ny,
 //   * set_flow_out(stream): one machine-readable line per slice,
-//   * set_quiet(): suppress the reference's per-slice dump of every past model.
+//   * set_quiet(): suppress the reference's per-slice dump of every past model,
+//   * set_device_ring(): keep the slice ring on the device (bf_ring_*): only new events are uploaded, a slice is an
+//     index range, and the warm-start chain is stream-ordered device work -- the host enqueues slices and reads the
+//     models back later (at once when the per-slice dump is printed).  Used when no per-event state is wanted
+//     (set_lazy_events, no accumulation); the events in `ev_buffer` then keep what Event::reset left, and noise
+//     marks of the tiny-window guard live on the device only.
 // Video / picture generation and the interactive mode are GUI features and are accepted but ignored.
 #ifndef BF_DVS_FLOW_H
 #define BF_DVS_FLOW_H
 
 #include <algorithm>
+#include <deque>
 #include <map>
 #include <memory>
 
@@ -71,6 +77,15 @@ protected:
     ull slices_done_;
     ull events_done_;
     ull iters_done_;
+    bool unsorted_ = false;                  // a timestamp decreased somewhere in the input (see get_accumulated)
+    // device-resident ring (set_device_ring)
+    bool device_ring_ = false;
+    bf_ring *ring_ = nullptr;
+    unsigned long ring_gen_ = 0;             // CudaDriver::generation() the ring was created under
+    int ring_pending_ = 64;
+    std::vector<bf_ring_event> ring_new_;    // events pushed since the last slice
+    struct Deferred { SliceLog log; int ticket; };
+    std::deque<Deferred> deferred_;          // slices enqueued on the device whose models have not been read back yet
 
 public:
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time = 0)
@@ -121,10 +136,14 @@ public:
     // buffer's events then keep what Event::reset left.  For callers that only want the per-slice models.
     void set_lazy_events(bool v = true) { lazy_events_ = v; }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
-    ObjectModel get_last_model() { return last_model; }
-    ull slices_done() const { return slices_done_; }
-    ull events_done() const { return events_done_; }
-    ull iterations_done() const { return iters_done_; }
+    void set_device_ring(bool v = true) { device_ring_ = v; }
+    bool device_ring_active() const {
+        return device_ring_ && lazy_events_ && !accumulate && !local_ && gpus_ == 1 && !(batch_ > 1 && stm_disable);
+    }
+    ObjectModel get_last_model() { resolve_deferred(); return last_model; }
+    ull slices_done() { resolve_deferred(); return slices_done_; }
+    ull events_done() { resolve_deferred(); return events_done_; }
+    ull iterations_done() { resolve_deferred(); return iters_done_; }
 
 protected:
     // dvs_flow.h:186-193: the oldest timestamp when the buffer overflowed, else now - SPAN
@@ -159,12 +178,20 @@ protected:
     }
 
     void run_pending();
+    void resolve_deferred();
+    void ring_slice(const SliceLog &log, ull start);
 };
 
 template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::add_event(Event &ev) {
     ev_buffer.push_back(ev);
     event_diff++;
+    if (ev.timestamp < current_slice_time) unsorted_ = true;
     current_slice_time = ev.timestamp;
+    if (device_ring_active()) {
+        bf_ring_event r;
+        r.fr_x = (uint16_t)ev.fr_x; r.fr_y = (uint16_t)(ev.fr_y | (ev.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = ev.timestamp;
+        ring_new_.push_back(r);
+    }
     time_diff = current_slice_time - last_slice_time;   // time only increases
     if ((event_diff < (sll)on_ev_change) && (time_diff < (sll)on_time_change)) return false;
     recompute();
@@ -218,12 +245,16 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
             for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) cur.push_back(ev_buffer[i]);
             accumulated.push_back(std::move(cur));
         }
+    } else if (device_ring_active()) {
+        ring_slice(log, start);
     } else if (batch_ > 1 && stm_disable) {
         // independent slice: snapshot it and minimise later together with its neighbours
         Pending p;
         p.slice_start = start;
         p.packed.resize(log.size);
         size_t k = 0;
+        // bounding box as set_cloud computes it (optimizer_rolling.h:252-260: minima start at RES_X / RES_Y, maxima at 0)
+        uint x_min = (uint)RES_X, y_min = (uint)RES_Y, x_max = 0, y_max = 0;
         for (auto &e : ev_buffer) {
             e.reset();
             e.set_local_time(start);
@@ -235,8 +266,18 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
             b.fr_x = (uint16_t)e.fr_x;
             b.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u));
             b.t_ns = (int32_t)e.t;
+            x_min = std::min(x_min, e.fr_x); x_max = std::max(x_max, e.fr_x);
+            y_min = std::min(y_min, e.fr_y); y_max = std::max(y_max, e.fr_y);
         }
         assert(k == log.size);
+        // run()'s tiny-window guard marks the slice's events as noise IN THE BUFFER (optimizer_rolling.h:49-55), and
+        // later overlapping slices skip them.  The batch is minimised later, so the same test (bf_guard_tiny in the
+        // back end, which will skip the slice) is evaluated here, before the next slice is snapshotted.
+        {
+            const int rows_img = scale * (int)(x_max - x_min) + scale, cols_img = scale * (int)(y_max - y_min) + scale;
+            if ((rows_img < scale * (int)RES_X / 15) && (cols_img < scale * (int)RES_Y / 15))
+                for (auto &e : ev_buffer) e.noise = true;
+        }
         p.log = log;
         if (accumulate) {
             p.copy.reserve(ev_buffer.size());
@@ -383,7 +424,69 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
     pending_.clear();
 }
 
-template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::flush() { run_pending(); }
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::flush() {
+    run_pending();
+    resolve_deferred();
+}
+
+// Default mode on the device-resident ring (include/bf_cuda.h: bf_ring_*).  Per slice the host uploads the events
+// that arrived since the last slice and enqueues "newest n events, local time relative to `start`, warm-started from
+// the previous slice's model ON THE DEVICE"; nothing here waits for the GPU unless the per-slice dump is wanted.
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const SliceLog &log, ull start) {
+    auto check = [](int rc, const char *what) {
+        if (rc < 0) {
+            std::cerr << what << " failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+    };
+    const long long cap = (long long)ev_buffer.capacity();
+    bf_ctx *ctx = CudaDriver::context(cap + 64, 1, scale);
+    if (!ring_ || ring_gen_ != CudaDriver::generation()) {
+        // (a context re-created for more capacity took its rings with it)
+        ring_ = bf_ring_create(ctx, cap, ring_pending_);
+        if (!ring_) check(-1, "bf_ring_create");
+        ring_gen_ = CudaDriver::generation();
+        // everything the buffer holds, oldest -> newest (the events of this slice included)
+        ring_new_.clear();
+        for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) {
+            const Event &e = ev_buffer[i];
+            bf_ring_event r;
+            r.fr_x = (uint16_t)e.fr_x; r.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = e.timestamp;
+            ring_new_.push_back(r);
+        }
+        for (auto &d : deferred_) (void)d;   // (tickets of a destroyed ring cannot be outstanding: resolve_deferred runs before a re-creation can be seen)
+    }
+    check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
+    ring_new_.clear();
+    if (log.size > 0) {
+        const sll t_new = (sll)(log.ts_first - start), t_old = (sll)(log.ts_last - start);
+        if (t_new > INT32_MAX || t_old > INT32_MAX || t_new < INT32_MIN || t_old < INT32_MIN) {
+            std::cerr << "DVS_flow: local time of an event exceeds +-2.1 s; shorten the slice" << std::endl;
+            std::exit(1);
+        }
+    }
+    const int ticket = bf_ring_slice(ring_, (int)log.size, start, scale, max_iter, stm_disable ? 0 : 1);
+    check(ticket, "bf_ring_slice");
+    deferred_.push_back(Deferred{log, ticket});
+    // the reference dumps every remembered slice after each recompute: that needs the model now
+    if (!quiet_ || (int)deferred_.size() >= ring_pending_ - 1) resolve_deferred();
+}
+
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::resolve_deferred() {
+    while (!deferred_.empty()) {
+        Deferred d = deferred_.front();
+        deferred_.pop_front();
+        bf_slice_result res;
+        if (bf_ring_result(ring_, d.ticket, &res) < 0) {
+            std::cerr << "bf_ring_result failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+        if (res.rc == BF_RC_DEGENERATE)
+            std::cerr << "OptimizerRolling: empty time image (the reference would not terminate here)" << std::endl;
+        d.log.model.from_pod(res.model);
+        log_slice(d.log, res.iters, res.rc);
+    }
+}
 
 // dvs_flow.h:350-389: concatenate the remembered slices, dropping from LATER slices every event that an
 // earlier slice already contains (same pixel, not newer, closer than 0.1 ms).  The reference does
@@ -392,6 +495,28 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
     flush();
     LinearEventCloudTemplate<Event> ret;
     std::cout << "Aggregating events into one cloud...\n";
+    if (unsorted_) {
+        // The indexed scan below equals the reference's nested scan only for non-decreasing timestamps (it stops at
+        // the first LATER BUFFER that starts after e, the reference only leaves the inner loop at the first newer
+        // event and still visits the buffers after it).  Out-of-order input takes the reference's literal scan.
+        for (ull i = 0; i < accumulated.size(); ++i) {
+            std::cout << "\tBuffer: " << i << "\n";
+            for (auto &e : accumulated[i]) {
+                if (e.t == -1) continue;
+                for (ull j = i + 1; j < accumulated.size(); ++j) {
+                    for (auto &o : accumulated[j]) {
+                        if (o - e > 0) break;
+                        if (o.t == -1) continue;
+                        if (e != o) continue;
+                        o.t = -1;
+                    }
+                }
+                ret.push_back(e);
+            }
+        }
+        std::cout << "FInal buffer contains " << ret.size() << " events." << std::endl;
+        return ret;
+    }
     // Per-buffer index "pixel -> positions, oldest first" (counting sort by pixel), built when a buffer is first
     // scanned and dropped once no earlier buffer can reach it any more: a few buffers are alive at a time.
     struct PixelIndex {

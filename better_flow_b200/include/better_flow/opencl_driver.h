@@ -42,7 +42,8 @@ public:
                           need_slices <= s.slices && need_scale <= s.scale;
         if (!fits) {
             const auto t0 = std::chrono::steady_clock::now();
-            if (s.ctx) bf_ctx_destroy(s.ctx);
+            if (s.ctx) bf_ctx_destroy(s.ctx);          // (destroys the context's rings with it)
+            s.generation += 1;
             s.rows = RES_X; s.cols = RES_Y;
             s.events = std::max<long long>(need_events + need_events / 4, 1 << 16);
             s.slices = std::max(need_slices, 64);
@@ -82,10 +83,14 @@ public:
         return s.multi;
     }
 
+    // bumped whenever the pooled context is (re)created: objects tied to the old context (bf_ring) are gone then
+    static unsigned long generation() { return state().generation; }
+
     static void shutdown() {
         State &s = state();
         if (s.ctx) bf_ctx_destroy(s.ctx);
         s.ctx = nullptr;
+        s.generation += 1;
         if (s.multi) bf_multi_destroy(s.multi);
         s.multi = nullptr;
     }
@@ -93,6 +98,7 @@ public:
 private:
     struct State {
         bf_ctx *ctx = nullptr;
+        unsigned long generation = 0;
         int rows = 0, cols = 0, slices = 0, scale = 3;
         long long events = 0;
         bf_multi *multi = nullptr;

@@ -36,6 +36,7 @@ static int sensor_w = 240, sensor_h = 180;
 static char *flowOutName = NULL;
 static int batch = 1;
 static int gpus = 1;
+static bool device_ring = true;
 static bool optimizer_local = false;
 static int device = 0;
 
@@ -72,6 +73,8 @@ static void usage(int ret) {
     printf("    [--sensor=WxH]\t\t\tSensor size in pixels (default = %ix%i)\n", sensor_w, sensor_h);
     printf("    [--flow-out=<name>]\t\t\tWrite one line per slice: id n iters rc total_dx total_dy total_rot total_div cx cy dx dy rot div cnt\n");
     printf("    [--batch=N]\t\t\t\tWith --stm-disable: minimise N slices per kernel launch (default = %i)\n", batch);
+    printf("    [--no-device-ring]\t\t\tKeep the slice ring on the host and hand every slice over in full (default without -o: the ring\n");
+    printf("              \t\t\t\tlives on the device, only new events are uploaded, warm starts chain on the device)\n");
     printf("    [--gpus=N]\t\t\t\tWith --stm-disable and --batch: deal every batch to N devices (starting at --device),\n");
     printf("              \t\t\t\tone launch per device and one NCCL all-gather of the per-slice flow (default = %i)\n", gpus);
     printf("    [--optimizer=rolling|local]\tPer-slice optimiser: OptimizerRolling (default, what the reference tool runs) or\n");
@@ -119,6 +122,7 @@ int main(int argc, char *argv[]) {
         else if (!strncmp(argv[i], "--flow-out=", 11)) flowOutName = argv[i] + 11;
         else if (!strncmp(argv[i], "--batch=", 8)) batch = atoi(argv[i] + 8);
         else if (!strncmp(argv[i], "--gpus=", 7)) gpus = atoi(argv[i] + 7);
+        else if (!strcmp(argv[i], "--no-device-ring")) device_ring = false;
         else if (!strcmp(argv[i], "--optimizer=local")) optimizer_local = true;
         else if (!strcmp(argv[i], "--optimizer=rolling")) optimizer_local = false;
         else if (!strncmp(argv[i], "--device=", 9)) device = atoi(argv[i] + 9);
@@ -153,7 +157,10 @@ int main(int argc, char *argv[]) {
     DVS_flow<EVENT_WIDTH, FROM_SEC(TIME_WIDTH)> estimator(event_refresh, FROM_SEC(time_refresh), 0, (size_t)max_events,
                                                           (sll)FROM_SEC(slice_time));
     if (outFileName != NULL) estimator.set_accumulate();
-    else estimator.set_lazy_events(true);   // nothing reads the per-event flow: skip its read-back (the per-slice models are unaffected)
+    else {
+        estimator.set_lazy_events(true);    // nothing reads the per-event flow: skip its read-back (the per-slice models are unaffected)
+        estimator.set_device_ring(device_ring);
+    }
     if (manual) estimator.set_manual_mode(true);
     if (img) estimator.set_generate_pictures(true, img_prefix);
     if (video) estimator.set_generate_video(true, video_name, video_fps);
@@ -174,6 +181,7 @@ int main(int argc, char *argv[]) {
     }
 
     const auto wall0 = std::chrono::steady_clock::now();
+    bool final_done = false;
     const size_t flen = strlen(file);
     const bool binary = flen > 4 && !strcmp(file + flen - 4, ".bin");
     if (binary) bufferize_file = true;   // binary input is always read up front
@@ -184,6 +192,7 @@ int main(int argc, char *argv[]) {
 
         clock_t begin = std::clock();
         clock_t begin_slice = std::clock();
+        const auto proc0 = std::chrono::steady_clock::now();
         ull i = 0;
         for (auto &e : ec) {
             ++i;
@@ -199,6 +208,16 @@ int main(int argc, char *argv[]) {
         }
         clock_t end = std::clock();
         std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;
+        if (timing) {
+            // wall time of the processing proper (events already in memory): add_event loop + the final slice + every
+            // model read back.  (The reference's figure above is std::clock(): CPU time, summed over threads.)
+            estimator.recompute();
+            estimator.flush();
+            final_done = true;
+            const double w = std::chrono::duration<double>(std::chrono::steady_clock::now() - proc0).count();
+            std::cerr << "[timing] processing " << i << " events in " << w << " s = " << double(i) / w / 1e6 << " Mev/s, slices "
+                      << estimator.slices_done() << std::endl;
+        }
     } else {
         std::cout << "Reading from file... (" << file << ")" << std::endl << std::flush;
         // block reader + from_chars (same values as `ifstream >>`), parsing one block ahead on a second thread
@@ -223,7 +242,7 @@ int main(int argc, char *argv[]) {
     }
 
     stamp("stream consumed");
-    estimator.recompute();   // ensure that *every* event has been processed
+    if (!final_done) estimator.recompute();   // ensure that *every* event has been processed
     estimator.flush();
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     if (!quiet)

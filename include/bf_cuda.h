@@ -251,6 +251,41 @@ int bf_multi_result(bf_multi *m, int slice, bf_slice_result *out);
 int bf_multi_locate(bf_multi *m, int slice, bf_ctx **ctx, int *slot, int *device);
 long long bf_multi_launch_count(bf_multi *m);
 
+
+/* ---- device-resident slice ring: DVS_flow's default mode ---------------------------------------
+ * Replaces, for the reference's default operating mode (overlapping 50 k-event / 200 ms windows re-minimised every
+ * 20 k events / 33 ms, each warm-started from the previous model), the per-slice hand-over of
+ * DVS_flow::recompute (dvs_flow.h:184-252): there every slice walks the whole CircularArray (datastructures.h:6-115)
+ * to build a LinearEventPtrs, resets / re-times every event, and -- with an accelerator behind AccelLib -- would
+ * re-upload the 60-95 % of the window it already sent for the previous slice (accel_lib.h:83-124 uploads per
+ * optimiser instance).  Here the ring lives on the device:
+ *   bf_ring_push    appends only the NEW events (absolute timestamps, 16-byte records) -- asynchronous H2D;
+ *   bf_ring_slice   enqueues "minimise the newest n events, local time = timestamp - slice_start"
+ *                   (OptimizerRolling::set_cloud / set_time / [set_model] / run, optimizer_rolling.h:236-299,48-125):
+ *                   a small kernel cuts the packed newest->oldest slice out of the ring (the order of
+ *                   dvs_flow.h:196-198), the persistent kernel minimises it.  With chain != 0 the warm start
+ *                   (set_model(last_model), dvs_flow.h:218-219) is taken ON THE DEVICE from the previous slice's
+ *                   result record, so the call returns without waiting for that slice: a whole warm-start chain is
+ *                   stream-ordered device work and the host only enqueues.  The tiny-window guard's noise marking
+ *                   (optimizer_rolling.h:49-55) is applied to the ring entries on the device as well.
+ *   bf_ring_result  waits for one slice and returns its record (tickets are results of bf_ring_slice, in order;
+ *                   a ticket stays readable until `max_pending` later slices have been enqueued).
+ * A ring belongs to one context and shares its stream, event buffer and images with the batch entry points (calls
+ * are serialised in stream order).  Per-event outputs are not available through the ring (use bf_minimize). */
+typedef struct bf_ring bf_ring;
+typedef struct bf_ring_event {
+    uint16_t fr_x, fr_y;     /* as in bf_event (fr_y may carry BF_EVENT_NOISE) */
+    uint32_t reserved;
+    uint64_t timestamp;      /* Event::timestamp, ns (event.h:13) */
+} bf_ring_event;
+bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending);
+void bf_ring_destroy(bf_ring *r);
+int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n);
+int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain);   /* -> ticket */
+int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out);
+int bf_ring_sync(bf_ring *r);
+long long bf_ring_pushed(bf_ring *r);   /* events appended so far */
+
 #ifdef __cplusplus
 }
 #endif

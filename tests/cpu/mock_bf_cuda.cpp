@@ -178,6 +178,73 @@ int bf_local_minimize(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, con
     return rc;
 }
 
+// ---- device-resident slice ring, restated on the host with the oracle as the minimiser ----
+}  // extern "C"
+struct bf_ring {
+    bf_ctx *c;
+    long long cap;
+    int max_pending;
+    std::vector<bf_ring_event> ring;      // event g of the stream at g % cap
+    long long pushed = 0;
+    std::vector<bf_slice_result> res;     // by ticket % max_pending
+    int next_ticket = 0;
+    bool have_prev = false;
+    bf_slice_result prev;
+    long long prev_lo = 0, prev_hi = 0;
+};
+static long long g_ring_pushes = 0, g_ring_slices = 0;
+extern "C" {
+long long bf_mock_ring_pushed_events(void) { return g_ring_pushes; }
+long long bf_mock_ring_slices(void) { return g_ring_slices; }
+
+bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
+    if (!c || capacity <= 0 || max_pending < 2) { g_err = "bf_ring_create: bad arguments"; return nullptr; }
+    bf_ring *r = new bf_ring;
+    r->c = c; r->cap = capacity; r->max_pending = max_pending;
+    r->ring.resize((size_t)capacity);
+    r->res.resize((size_t)max_pending);
+    memset(&r->prev, 0, sizeof r->prev);
+    return r;
+}
+void bf_ring_destroy(bf_ring *r) { delete r; }
+long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
+int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (ev[i].fr_x >= r->c->rows || (ev[i].fr_y & 0x7fffu) >= r->c->cols) { g_err = "event outside the sensor"; return BF_ERR_ARG; }
+        r->ring[(size_t)(r->pushed % r->cap)] = ev[i];
+        r->pushed += 1;
+    }
+    g_ring_pushes += n;
+    return BF_OK;
+}
+int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain) {
+    if (n < 0 || n > r->cap || n > r->pushed) { g_err = "bf_ring_slice: n exceeds the ring's content"; return BF_ERR_ARG; }
+    MockSlice s;
+    s.fx.resize(n); s.fy.resize(n); s.t.resize(n); s.noise.resize(n);
+    const bool prev_noise = r->have_prev && (r->prev.flags & BF_FLAG_ALL_NOISE);
+    for (int i = 0; i < n; ++i) {
+        const long long g = r->pushed - 1 - i;
+        bf_ring_event &e = r->ring[(size_t)(g % r->cap)];
+        if (prev_noise && g >= r->prev_lo && g < r->prev_hi) e.fr_y |= BF_EVENT_NOISE;
+        s.fx[i] = e.fr_x; s.fy[i] = (uint16_t)(e.fr_y & 0x7fffu); s.noise[i] = (e.fr_y & BF_EVENT_NOISE) ? 1 : 0;
+        s.t[i] = (int64_t)(e.timestamp - slice_start);
+    }
+    s.scale = scale; s.max_iter = max_iter; s.has_init = chain != 0;
+    if (chain) s.init = r->prev.model;     // (all-zero for the first slice: last_model of a fresh DVS_flow)
+    run_slice(r->c, s);
+    const int ticket = r->next_ticket++;
+    r->res[(size_t)(ticket % r->max_pending)] = s.res;
+    r->prev = s.res; r->have_prev = true; r->prev_lo = r->pushed - n; r->prev_hi = r->pushed;
+    g_ring_slices += 1;
+    return ticket;
+}
+int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out) {
+    if (ticket < 0 || ticket >= r->next_ticket || ticket < r->next_ticket - r->max_pending) { g_err = "bad ticket"; return BF_ERR_ARG; }
+    *out = r->res[(size_t)(ticket % r->max_pending)];
+    return BF_OK;
+}
+int bf_ring_sync(bf_ring *) { return BF_OK; }
+
 // entry points the mirror references but these tests never reach
 static int unavailable(const char *what) { g_err = std::string(what) + ": not part of the CPU test double"; return BF_ERR_STATE; }
 int bf_time_img(bf_ctx *, int, const double *, const double *, const int32_t *, const uint8_t *, int, int, int, int, int, float *) { return unavailable("bf_time_img"); }

@@ -28,6 +28,7 @@ template <class Flow>
 int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint64_t *ts, int scale, int max_iter, int stm_disable,
         int flush, int batch, int local, int lazy, int max_slices, double *models, long long *info, double *uv) {
     est.set_lazy_events(lazy != 0);
+    est.set_device_ring(lazy == 2);          // lazy == 2: the slice ring lives behind the C ABI (bf_ring_*)
     est.set_scale(scale);
     est.set_max_iter(max_iter);
     est.set_stm_disable(stm_disable != 0);

@@ -126,3 +126,29 @@ def test_batched_tool_writes_the_same_flow_file(mock_cli, tmp_path):
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append((open(uv, "rb").read(), open(fl).read()))
     assert outs[0] == outs[1] and len(outs[0][1].splitlines()) >= 6 and len(outs[0][0]) > 100000
+
+
+def test_out_of_order_input_still_equals_the_reference_tool(mock_cli, tmp_path):
+    """Timestamps that DEcrease here and there (sensor jitter, merged recordings): the -o aggregation falls back to
+    the reference's literal nested scan (dvs_flow.h:350-389), whose result the indexed scan only reproduces for sorted
+    input -- the files must stay byte-identical."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/bf_motion_compensator_ref not built (no /root/reference here)")
+    import numpy as np
+    from better_flow_b200 import synth
+    st = synth.make_stream(240, 180, 0.6e6, 0.05, seed=29, vel=(-70.0, 30.0))
+    t = st.t_ns.copy()
+    rng = np.random.default_rng(4)
+    for k in rng.integers(100, len(t) - 100, 60):          # swap 60 neighbouring pairs and push a few events 2 ms back
+        t[k], t[k + 1] = t[k + 1], t[k]
+    for k in rng.integers(2000, len(t) - 100, 12):
+        t[k] = max(0, t[k] - 2_000_000)
+    st.t_ns = t
+    txt = tmp_path / "events.txt"
+    st.to_text(str(txt))
+    o_ref, o_new = tmp_path / "ref_uv.txt", tmp_path / "new_uv.txt"
+    ref = subprocess.run([REF_CLI, "-o", str(o_ref), str(txt)], capture_output=True, text=True, timeout=600)
+    new = subprocess.run([mock_cli, "-o", str(o_new), str(txt)], capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0 and new.returncode == 0, (ref.stderr[-500:], new.stderr[-1500:])
+    assert open(o_ref, "rb").read() == open(o_new, "rb").read() and os.path.getsize(o_ref) > 100000
+    assert _stable(ref.stdout, o_ref, txt) == _stable(new.stdout, o_new, txt)

@@ -34,6 +34,8 @@ def hs():
     lib = C.CDLL(so)
     lib.bf_mock_minimize_calls.restype = C.c_longlong
     lib.bf_mock_batch_runs.restype = C.c_longlong
+    lib.bf_mock_ring_pushed_events.restype = C.c_longlong
+    lib.bf_mock_ring_slices.restype = C.c_longlong
     return lib
 
 
@@ -46,7 +48,7 @@ def run_host(lib, fr_x, fr_y, ts, config=0, ev_refresh=20000, time_refresh_ns=33
     p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
     k = lib.st_stream(config, len(fx), p(fx, C.c_uint32), p(fy, C.c_uint32), p(t, C.c_uint64), C.c_ulonglong(ev_refresh),
                       C.c_ulonglong(time_refresh_ns), scale, max_iter, 1 if stm_disable else 0, 1 if flush else 0, batch,
-                      1 if local else 0, 1 if lazy else 0, max_slices, p(models, C.c_double), p(info, C.c_longlong), p(uv, C.c_double))
+                      1 if local else 0, int(lazy), max_slices, p(models, C.c_double), p(info, C.c_longlong), p(uv, C.c_double))
     assert 0 <= k <= max_slices
     return models[:k], info[:k], uv[:k]
 
@@ -147,3 +149,59 @@ def test_optimizer_local_mode_against_the_compiled_class(hs):
         want = ref.local_minimize(fr_x[idx], fr_y[idx], ts[idx] - start, scale=3)
         assert m[7] == -want["nx"] and m[8] == -want["ny"] and m[2] == want["score"], (i.tolist(), m[7:9], want["nx"], want["ny"])
     assert np.any(models[:, 7] != 0)
+
+
+def test_batched_tiny_window_marks_noise_like_the_unbatched_path(hs):
+    """--stm-disable --batch=N: a slice that trips the tiny-window guard (optimizer_rolling.h:49-55) must mark its
+    events as noise in the live buffer BEFORE the next overlapping slice is snapshotted, exactly as the unbatched
+    path and the reference do -- the batch itself is minimised later."""
+    rng = np.random.default_rng(3)
+    n0 = 12000
+    fx0, fy0 = rng.integers(80, 88, n0), rng.integers(100, 110, n0)     # first 12 k events: a tiny window (-> all noise)
+    st = synth.make_stream(240, 180, 1.0e6, 0.06, seed=14)              # then a normal scene, overlapping slices
+    fx = np.concatenate([fx0, st.y]); fy = np.concatenate([fy0, st.x])
+    t = np.concatenate([np.sort(rng.integers(10 ** 9, 10 ** 9 + 10 ** 7, n0)), st.t_ns + 10 ** 9 + 10 ** 7]).astype(np.uint64)
+    a, ia, _ = run_host(hs, fx, fy, t, ev_refresh=10000, stm_disable=True, max_iter=4)
+    b, ib, _ = run_host(hs, fx, fy, t, ev_refresh=10000, stm_disable=True, max_iter=4, batch=4)
+    assert len(a) == len(b) >= 5
+    assert np.array_equal(a, b), np.abs(a - b).max()
+    assert np.all(a[1][7:] == 0) and np.any(a[-1] != 0)                  # the guard fired early on, later slices ran
+    from oracle import ref
+    if ref.available(180, 240):
+        want, _ = ref.stream(fx, fy, t, config=0, ev_refresh=10000, scale=3, max_iter=4, stm_disable=True, flush=True)
+        assert np.array_equal(b, want)
+
+
+@pytest.mark.parametrize("config,stm", [(0, False), (0, True), (1, False)])
+def test_device_ring_mode_changes_no_model(hs, config, stm):
+    """set_device_ring (the CLI's default without -o): the ring lives behind the C ABI, the host pushes only the NEW
+    events of every slice and enqueues "the newest n events" -- warm starts chain behind the ABI, models are read back
+    late.  Same models as the host-driven path; exactly the stream's events cross the ABI once."""
+    st = synth.make_stream(240, 180, 1.0e6, 0.16, seed=47, vel=(-60.0, 90.0), omega=0.5)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    a, ia, _ = run_host(hs, fr_x, fr_y, ts, config=config, stm_disable=stm, max_iter=6, lazy=1)
+    c0, p0, s0 = hs.bf_mock_minimize_calls(), hs.bf_mock_ring_pushed_events(), hs.bf_mock_ring_slices()
+    b, ib, uvb = run_host(hs, fr_x, fr_y, ts, config=config, stm_disable=stm, max_iter=6, lazy=2)
+    assert len(a) == len(b) >= 6 and ia.tolist() == ib.tolist()
+    assert np.array_equal(a, b), np.abs(a - b).max()
+    assert hs.bf_mock_minimize_calls() == c0                               # no per-slice hand-over any more
+    assert hs.bf_mock_ring_slices() - s0 == len(b)
+    assert hs.bf_mock_ring_pushed_events() - p0 == len(ts)                 # every event uploaded exactly once
+    from oracle import ref
+    if ref.available(180, 240):
+        want, _ = ref.stream(fr_x, fr_y, ts, config=config, scale=3, max_iter=6, stm_disable=stm, flush=True)
+        assert np.array_equal(b, want)
+
+
+def test_device_ring_tiny_window_noise(hs):
+    """The tiny-window guard's noise marks live behind the ABI in ring mode: later overlapping slices skip the events."""
+    rng = np.random.default_rng(3)
+    n0 = 12000
+    fx0, fy0 = rng.integers(80, 88, n0), rng.integers(100, 110, n0)
+    st = synth.make_stream(240, 180, 1.0e6, 0.06, seed=14)
+    fx = np.concatenate([fx0, st.y]); fy = np.concatenate([fy0, st.x])
+    t = np.concatenate([np.sort(rng.integers(10 ** 9, 10 ** 9 + 10 ** 7, n0)), st.t_ns + 10 ** 9 + 10 ** 7]).astype(np.uint64)
+    for stm in (False, True):
+        a, _, _ = run_host(hs, fx, fy, t, ev_refresh=10000, stm_disable=stm, max_iter=4, lazy=1)
+        b, _, _ = run_host(hs, fx, fy, t, ev_refresh=10000, stm_disable=stm, max_iter=4, lazy=2)
+        assert len(a) == len(b) >= 5 and np.array_equal(a, b)
