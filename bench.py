@@ -446,16 +446,17 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, em = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(k):
                 fn()
+            em.record(stream)                         # this rank's own work ends here; the collective below waits for every rank
             flush_gather()                            # the one all_gather of these k steps' records: inside the timed region
             e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        own = ms
+        own = e0.elapsed_time(em)
         if dist is not None:
             t = torch.tensor([ms], device=DEV, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -521,7 +522,7 @@ def main():
         allst = allst.cpu().numpy()
         tot_events = int(allst[:, 4].sum())
         gather_ok = bool(allst[:, 6].min() > 0.5)
-        per_rank = [{"rank": r, "ms_per_step": float(allst[r, 0]), "e2e_ms_per_step": float(allst[r, 1]), "sum_iters": int(allst[r, 2]),
+        per_rank = [{"rank": r, "own_ms_per_step": float(allst[r, 0]), "own_e2e_ms_per_step": float(allst[r, 1]), "sum_iters": int(allst[r, 2]),
                      "event_iters": int(allst[r, 3]), "events": int(allst[r, 4]), "slices": int(allst[r, 5])} for r in range(world)]
     value = tot_events * args.steps / ms_res / 1e3
     e2e_val = tot_events * args.steps / ms_e2e / 1e3

@@ -65,6 +65,7 @@ ABI_SYMBOLS = (
     "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
+    "bf_projection_img",
     "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed",
 )
 
@@ -136,6 +137,7 @@ def load() -> C.CDLL:
         lib.bf_multi_locate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.bf_multi_launch_count.argtypes = [C.c_void_p]
         lib.bf_multi_launch_count.restype = C.c_longlong
+        lib.bf_projection_img.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.bf_ring_create.restype = C.c_void_p
         lib.bf_ring_create.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
         lib.bf_ring_destroy.argtypes = [C.c_void_p]
@@ -368,6 +370,16 @@ class Context:
         self.lib.bf_model_from_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self._chk(self.lib.bf_model_from_image(self.h, im.shape[0], im.shape[1], _ptr(im), _ptr(out7), _ptr(gx), _ptr(gy)))
         return (out7, gx, gy) if want_grad else out7
+
+    def projection_img(self, pr_x, pr_y, scale=3, noise=None):
+        """EventFile::projection_img: (uint8 image [rows * scale, cols * scale], nonzero average before scaling)."""
+        px = np.ascontiguousarray(pr_x, dtype=np.float64)
+        py = np.ascontiguousarray(pr_y, dtype=np.float64)
+        nz = np.ascontiguousarray(noise, dtype=np.uint8) if noise is not None else None
+        out = np.zeros((self.rows * scale, self.cols * scale), dtype=np.uint8)
+        avg = np.zeros(1)
+        self._chk(self.lib.bf_projection_img(self.h, len(px), _ptr(px), _ptr(py), _ptr(nz), scale, _ptr(out), _ptr(avg)))
+        return out, float(avg[0])
 
     def project(self, fr_x, fr_y, t_ns, pr_x, pr_y, dnx, dny, cx, cy, div, crl):
         fx = np.ascontiguousarray(fr_x, dtype=np.uint16)

@@ -679,6 +679,79 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
     }
 }
 
+// ---- EventFile::projection_img (event_file.h:460-515) -------------------------------------------------------------
+// Not a performance path (debug images): four plain per-event / per-pixel kernels.
+__global__ void bf_proj_splat_kernel(int n, const double *pr_x, const double *pr_y, const unsigned char *noise, int scale,
+                                     int res_x, int res_y, unsigned *cnt, int cols) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (noise && noise[i]) continue;
+        const double fx = __dmul_rn(pr_x[i], (double)scale), fy = __dmul_rn(pr_y[i], (double)scale);
+        if (!(fx == fx) || !(fy == fy)) continue;                      // x86 cvttsd2si gives INT_MIN for NaN: rejected by x < 0
+        const int x = __double2int_rz(fx), y = __double2int_rz(fy);    // (saturating: +-huge values are rejected below either way)
+        if (x >= scale * (res_x - 1) || x < 0 || y >= scale * (res_y - 1) || y < 0) continue;   // :486-487
+        atomicAdd(cnt + (size_t)(x + scale / 2) * cols + (y + scale / 2), 1u);                 // point count; the block splat is the box sum below
+    }
+}
+// saturating scale x scale block splat = min(255, box sum of the point counts)
+__global__ void bf_proj_box_kernel(const unsigned *cnt, int rows, int cols, int h, unsigned char *img) {
+    const long long P = (long long)rows * cols;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / cols), j = (int)(k - (long long)i * cols);
+        unsigned s = 0;
+        for (int a = max(i - h, 0); a <= min(i + h, rows - 1); ++a)
+            for (int b = max(j - h, 0); b <= min(j + h, cols - 1); ++b) s += cnt[(size_t)a * cols + b];
+        img[k] = (unsigned char)min(s, 255u);
+    }
+}
+__device__ __forceinline__ int reflect101(int i, int n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+// cv::GaussianBlur(k x k, sigma 0) on CV_8UC1: OpenCV's fixed table for k <= 7 -- [1 2 1]/4 and [1 4 6 4 1]/16 -- in
+// fixed point, rounded once after both passes, BORDER_REFLECT_101 (pinned on the real cv2 in tests/golden); plus the
+// nonzero count / sum of the result (EventFile::nonzero_average)
+__global__ void bf_proj_blur_kernel(const unsigned char *img, int rows, int cols, int k, unsigned char *out, unsigned long long *nz) {
+    const int w3[3] = {1, 2, 1}, w5[5] = {1, 4, 6, 4, 1};
+    const int r = k / 2, shift = k == 1 ? 0 : (k == 3 ? 4 : 8);
+    unsigned long long my_cnt = 0, my_sum = 0;
+    const long long P = (long long)rows * cols;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q / cols), j = (int)(q - (long long)i * cols);
+        int s = 0;
+        if (k == 1) s = img[q];
+        else
+            for (int a = -r; a <= r; ++a) {
+                const int wa = k == 3 ? w3[a + r] : w5[a + r];
+                const unsigned char *row = img + (size_t)reflect101(i + a, rows) * cols;
+                int t = 0;
+                for (int b = -r; b <= r; ++b) t += (k == 3 ? w3[b + r] : w5[b + r]) * row[reflect101(j + b, cols)];
+                s += wa * t;
+            }
+        const unsigned char v = (unsigned char)((s + ((1 << shift) >> 1)) >> shift);
+        out[q] = v;
+        if (v) { my_cnt += 1; my_sum += v; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_cnt += __shfl_xor_sync(0xffffffffu, my_cnt, o);
+        my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && my_cnt) { atomicAdd(nz, my_cnt); atomicAdd(nz + 1, my_sum); }
+}
+// cv::convertScaleAbs(img, img, 127 / avg, 0) for CV_8U: saturate_cast<uchar>(|float(src) * float(alpha)|), round-half-even
+__global__ void bf_proj_scale_kernel(unsigned char *img, long long P, const unsigned long long *nz, double *avg_out) {
+    const unsigned long long c = nz[0], s = nz[1];
+    const double avg = c ? (double)s / (double)c : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && avg_out) *avg_out = avg;
+    if (c == 0) return;
+    const float alpha = (float)(127.0 / avg);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < P; q += (long long)gridDim.x * blockDim.x) {
+        const int v = __float2int_rn(fabsf(__fmul_rn((float)img[q], alpha)));
+        img[q] = (unsigned char)min(v, 255);
+    }
+}
+
 // ---- device-resident slice ring (include/bf_cuda.h: bf_ring_*) -------------------------------------------------
 // Cuts "the newest n events, newest -> oldest, local time = timestamp - start" (what a range-for over the
 // reference's CircularArray hands to the optimiser, dvs_flow.h:196-198 + Event::set_local_time, event.h:61-63) out of
@@ -773,6 +846,7 @@ struct bf_ctx {
     int n_groups_alloc = 0;
     int iter_cap = 20000;
     int min_events = 1000;
+    int smem_pad = 0;           // experiment knob: extra dynamic shared memory per CTA (shrinks the L1 carve-out)
     int tail_help = 1;          // idle groups join slices that are still running when the queue is empty
     int max_grow = 8;           // ... up to this many groups per slice
 
@@ -832,9 +906,9 @@ static int tma_tile_elems_of(const bf_ctx *c) { return (BF_CELL_ROWS + 2 * (c->m
 static size_t tma_off_of(const bf_ctx *c) { return (smem_tables_end(c) + 127) & ~(size_t)127; }
 static size_t smem_bytes_min(const bf_ctx *c) {
 #if BF_TMA_PATCH
-    return tma_off_of(c) + (size_t)BF_NW * tma_tile_elems_of(c) * sizeof(u64);
+    return tma_off_of(c) + (size_t)BF_NW * tma_tile_elems_of(c) * sizeof(u64) + (size_t)c->smem_pad;
 #else
-    return smem_tables_end(c);
+    return smem_tables_end(c) + (size_t)c->smem_pad;
 #endif
 }
 
@@ -1082,6 +1156,11 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "min_group")) c->min_group = (int)std::max(1LL, value);
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
+    else if (!strcmp(key, "smem_pad")) {
+        c->smem_pad = (int)std::max(0LL, std::min(value, 64LL * 1024));
+        CU(cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
+        CU(cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
+    }
     else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
     else if (!strcmp(key, "max_grow")) c->max_grow = (int)std::min<long long>(BF_MAX_GROW, std::max(1LL, value));
     else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
@@ -1604,6 +1683,43 @@ int bf_project(bf_ctx *c, int n, const uint16_t *fr_x, const uint16_t *fr_y, con
     CU(cudaMemcpyAsync(pr_y, base + o_py, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (nx) CU(cudaMemcpyAsync(nx, base + o_nx, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (ny) CU(cudaMemcpyAsync(ny, base + o_ny, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_projection_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const uint8_t *noise, int scale, uint8_t *out,
+                      double *nz_avg) {
+    if (!c || n < 0 || (n > 0 && (!pr_x || !pr_y)) || !out) return fail(BF_ERR_ARG, "bf_projection_img: bad arguments");
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported (1, 3 or 5)", scale);
+    CU(cudaSetDevice(c->device));
+    const int rows = c->res_x * scale, cols = c->res_y * scale;
+    const size_t P = (size_t)rows * cols;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_px = take((size_t)n * 8), o_py = take((size_t)n * 8), o_nz = take((size_t)n), o_cnt = take(P * 4);
+    const size_t o_a = take(P), o_b = take(P), o_acc = take(16), o_avg = take(8);
+    int rc;
+    if ((rc = stage_alloc(c, off)) != BF_OK) return rc;
+    unsigned char *base = (unsigned char *)c->d_stage;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(base + o_px, pr_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(base + o_py, pr_y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        if (noise) CU(cudaMemcpyAsync(base + o_nz, noise, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(base + o_cnt, 0, P * 4, c->stream));
+    CU(cudaMemsetAsync(base + o_acc, 0, 16 + 256, c->stream));
+    const int gb = std::max(1, std::min(8 * c->sms, (int)((P + 255) / 256)));
+    if (n > 0)
+        bf_proj_splat_kernel<<<std::max(1, std::min(4 * c->sms, (n + 255) / 256)), 256, 0, c->stream>>>(
+            n, (const double *)(base + o_px), (const double *)(base + o_py), noise ? base + o_nz : nullptr, scale, c->res_x, c->res_y,
+            (unsigned *)(base + o_cnt), cols);
+    bf_proj_box_kernel<<<gb, 256, 0, c->stream>>>((const unsigned *)(base + o_cnt), rows, cols, scale / 2, base + o_a);
+    bf_proj_blur_kernel<<<gb, 256, 0, c->stream>>>(base + o_a, rows, cols, scale, base + o_b, (unsigned long long *)(base + o_acc));
+    bf_proj_scale_kernel<<<gb, 256, 0, c->stream>>>(base + o_b, (long long)P, (const unsigned long long *)(base + o_acc), (double *)(base + o_avg));
+    c->launches += n > 0 ? 4 : 3;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, base + o_b, P, cudaMemcpyDeviceToHost, c->stream));
+    if (nz_avg) CU(cudaMemcpyAsync(nz_avg, base + o_avg, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return BF_OK;
 }

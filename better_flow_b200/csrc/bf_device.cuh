@@ -28,6 +28,14 @@
 
 #include "bf_logic.h"
 
+// The passes of the minimise kernel are inlined into every instance of the slice loop (3 scales x own slice / helped
+// slice); left to its heuristics the compiler stops inlining them once the kernel grows (measured with the TMA
+// variant: event_pass became a real call, its arguments went through a 592-byte stack frame, the event pass took
+// +79 %).  BF_PASS_INLINE pins the decision.
+#ifndef BF_PASS_INLINE
+#define BF_PASS_INLINE __forceinline__
+#endif
+
 // ---- compile-time geometry -------------------------------------------------------------------
 #ifndef BF_NT
 #define BF_NT 512              // threads per CTA (16 warps)
@@ -493,7 +501,7 @@ __device__ __forceinline__ void event_one(const EventCtx &c, uint2 e, float2 &st
 }
 
 template <int SH>
-__device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
+__device__ BF_PASS_INLINE void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &g, const BfPack &pk,
                            const BfProj &q, int rank, int G, bool first, bool project, u64 *img_new,
                            double2 *out_nxy, unsigned *flags, unsigned tag, const int2 *row_tab, const short2 *col_tab,
                            unsigned *bm = nullptr) {
@@ -563,7 +571,9 @@ __device__ void event_pass(const KParams &P, const SliceDesc &sd, const BfGeom &
 //     the exact quotient by < 2^-23 ulp, and (ii) s/c with c < 2^17 is never closer than 2^-18 ulp
 //     to a rounding boundary without lying on it, which it cannot (c*(25-bit odd) has no 24-bit
 //     representation).  tests/test_divconst.py checks the sequence against IEEE division.
+#ifndef BF_RCP_TAB
 #define BF_RCP_TAB 1024
+#endif
 __device__ __forceinline__ void fill_rcp_table(float2 *tab) {
     for (int c = threadIdx.x; c < BF_RCP_TAB; c += blockDim.x) {
         const float cf = (float)c;
@@ -850,7 +860,7 @@ template <int SH> __device__ __forceinline__ void local_cell_process(Acc &acc, c
 // MODE 0: mean-timestamp image + Scharr + moments (OptimizerRolling); MODE 1: saturated event-count
 // image + Gaussian blur + non-zero mean (OptimizerLocal, see local_cell_process).
 template <int SH, bool MATERIALISE, int MODE = 0>
-__device__ int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
+__device__ BF_PASS_INLINE int image_pass(Acc &acc, const u64 *img, int pitch, const BfGeom &g, const BfPack &pk,
                           const float2 *rcp_tab, const unsigned *flags, unsigned tag, int rank, int G, unsigned short *list,
                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
                           const unsigned *flags_clear, unsigned tag_clear, const unsigned short *list_prev,

@@ -41,6 +41,17 @@ public:
         newest_ = &store_[head_];
     }
 
+    // push_back that copies only what DType::copy_header_to copies (for an Event: coordinates, times, noise / valid
+    // flags -- the first 26 of its 152 bytes); the slot's other fields keep their old contents.  Used by DVS_flow when
+    // the slices are cut on the device and nothing on the host ever reads the per-event state (set_device_ring).
+    void push_back_header(const DType &d) {
+        span_ok_ = false;
+        if (count_ < cap_) ++count_;
+        head_ = (head_ + 1 >= cap_) ? 0 : head_ + 1;
+        d.copy_header_to(store_[head_]);
+        newest_ = &store_[head_];
+    }
+
     // idx counts back from the newest element
     DType &operator[](size_t idx) {
         assert(idx < count_);

@@ -16,16 +16,24 @@
 //   * set_device_ring(): keep the slice ring on the device (bf_ring_*): only new events are uploaded, a slice is an
 //     index range, and the warm-start chain is stream-ordered device work -- the host enqueues slices and reads the
 //     models back later (at once when the per-slice dump is printed).  Used when no per-event state is wanted
-//     (set_lazy_events, no accumulation); the events in `ev_buffer` then keep what Event::reset left, and noise
-//     marks of the tiny-window guard live on the device only.
-// Video / picture generation and the interactive mode are GUI features and are accepted but ignored.
+//     (set_lazy_events, no accumulation); `ev_buffer` then maintains only the identity of its events (coordinates,
+//     timestamp, flags: Event::copy_header_to), and noise marks of the tiny-window guard live on the device only.
+//   * set_generate_pictures / set_generate_video (the reference's --img / --video, dvs_flow.h:256-335): after every
+//     slice a 2 x 2 montage is written -- EventFile::projection_img of the events as recorded and as warped (computed
+//     on the device: bf_projection_img), next to the corresponding mean-timestamp images (bf_time_img) where the
+//     reference puts its HSV-coloured time images.  Without OpenCV there is no JPEG / AVI encoder and no text
+//     rendering: pictures are binary PGM files (frame_N.pgm) with the overlay text of the reference's frames in a
+//     sidecar frame_N.txt, the video is an uncompressed YUV4MPEG2 stream (mono), playable by ffplay / mpv.
+// The interactive mode is a GUI feature and is accepted but ignored.
 #ifndef BF_DVS_FLOW_H
 #define BF_DVS_FLOW_H
 
 #include <algorithm>
 #include <deque>
+#include <fstream>
 #include <map>
 #include <memory>
+#include <sstream>
 
 #include <better_flow/common.h>
 #include <better_flow/event.h>
@@ -78,8 +86,16 @@ protected:
     ull events_done_;
     ull iters_done_;
     bool unsorted_ = false;                  // a timestamp decreased somewhere in the input (see get_accumulated)
+    bool generate_pictures_ = false, generate_video_ = false;
+    std::string img_prefix_ = "./", video_name_ = "out.avi";
+    int video_fps_ = 30;
+    ull frame_count_ = 0;
+    std::unique_ptr<std::ofstream> video_out_;
+    void dump_frame(size_t n_slice);
     // device-resident ring (set_device_ring)
     bool device_ring_ = false;
+    bool ring_on_ = false;                   // device_ring_active(), re-evaluated by every setter it depends on
+    void update_ring_on() { ring_on_ = device_ring_ && lazy_events_ && !accumulate && !local_ && gpus_ == 1 && !(batch_ > 1 && stm_disable); }
     bf_ring *ring_ = nullptr;
     unsigned long ring_gen_ = 0;             // CudaDriver::generation() the ring was created under
     int ring_pending_ = 64;
@@ -107,7 +123,7 @@ public:
     void recompute();
     void flush();   // minimise whatever is still queued (batch mode)
 
-    void set_accumulate(bool val = true) { accumulate = val; }
+    void set_accumulate(bool val = true) { accumulate = val; update_ring_on(); }
     LinearEventCloudTemplate<Event> get_accumulated();
     void set_manual_mode(bool val = true) {
         manual_mode = val;
@@ -115,31 +131,31 @@ public:
     }
     void set_max_iter(int val = -1) { max_iter = val; }
     void set_scale(int val = 3) { scale = val; }
-    void set_generate_video(bool val = true, std::string = "out.avi", int = 30) {
-        if (val) std::cerr << "video output is a visualisation feature of the reference and is ignored" << std::endl;
+    void set_generate_video(bool val = true, std::string fname = "out.avi", int fps = 30) {
+        generate_video_ = val; video_name_ = fname; video_fps_ = fps;
+        if (val) std::cerr << "video output: uncompressed YUV4MPEG2 (mono) stream in '" << fname << "' (no AVI encoder without OpenCV)" << std::endl;
     }
-    void set_generate_pictures(bool val = true, std::string = "./") {
-        if (val) std::cerr << "picture output is a visualisation feature of the reference and is ignored" << std::endl;
+    void set_generate_pictures(bool val = true, std::string prefix = "./") {
+        generate_pictures_ = val; img_prefix_ = prefix;
+        if (val) std::cerr << "picture output: " << prefix << "/frame_N.pgm + frame_N.txt (no JPEG encoder without OpenCV)" << std::endl;
     }
-    void set_stm_disable(bool val = true) { stm_disable = val; }
+    void set_stm_disable(bool val = true) { stm_disable = val; update_ring_on(); }
 
     sll get_buf_size() { return ev_buffer.size(); }
     sll get_time_diff() { return time_diff; }
     sll get_buf_time_diff() { return current_slice_time - slice_start_time(); }
 
     // extensions
-    void set_batch(int n) { batch_ = n < 1 ? 1 : n; }
-    void set_gpus(int n) { gpus_ = n < 1 ? 1 : n; }
-    void set_optimizer_local(bool v = true) { local_ = v; }
+    void set_batch(int n) { batch_ = n < 1 ? 1 : n; update_ring_on(); }
+    void set_gpus(int n) { gpus_ = n < 1 ? 1 : n; update_ring_on(); }
+    void set_optimizer_local(bool v = true) { local_ = v; update_ring_on(); }
     void set_quiet(bool q = true) { quiet_ = q; }
     // Do not read the per-event state (pr, nx/ny, u/v) back after a slice unless it is being accumulated: the
     // buffer's events then keep what Event::reset left.  For callers that only want the per-slice models.
-    void set_lazy_events(bool v = true) { lazy_events_ = v; }
+    void set_lazy_events(bool v = true) { lazy_events_ = v; update_ring_on(); }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
-    void set_device_ring(bool v = true) { device_ring_ = v; }
-    bool device_ring_active() const {
-        return device_ring_ && lazy_events_ && !accumulate && !local_ && gpus_ == 1 && !(batch_ > 1 && stm_disable);
-    }
+    void set_device_ring(bool v = true) { device_ring_ = v; update_ring_on(); }
+    bool device_ring_active() const { return ring_on_; }
     ObjectModel get_last_model() { resolve_deferred(); return last_model; }
     ull slices_done() { resolve_deferred(); return slices_done_; }
     ull events_done() { resolve_deferred(); return events_done_; }
@@ -183,15 +199,20 @@ protected:
 };
 
 template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::add_event(Event &ev) {
-    ev_buffer.push_back(ev);
-    event_diff++;
-    if (ev.timestamp < current_slice_time) unsorted_ = true;
-    current_slice_time = ev.timestamp;
-    if (device_ring_active()) {
+    const bool on_device = device_ring_active();
+    if (on_device) {
+        // the slices are cut on the device: the host ring only has to know WHICH events it holds (triggers, eviction,
+        // slice start, a rebuild of the device ring) -- 26 bytes per event instead of the 152-byte record
+        ev_buffer.push_back_header(ev);
         bf_ring_event r;
         r.fr_x = (uint16_t)ev.fr_x; r.fr_y = (uint16_t)(ev.fr_y | (ev.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = ev.timestamp;
         ring_new_.push_back(r);
+    } else {
+        ev_buffer.push_back(ev);
     }
+    event_diff++;
+    if (ev.timestamp < current_slice_time) unsorted_ = true;
+    current_slice_time = ev.timestamp;
     time_diff = current_slice_time - last_slice_time;   // time only increases
     if ((event_diff < (sll)on_ev_change) && (time_diff < (sll)on_time_change)) return false;
     recompute();
@@ -340,6 +361,7 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
             for (auto &e : ev_buffer) e.noise = true;         // (the flag outlives the slice: later slices skip these events)
         }
         log_slice(log, res.iters, rc);
+        if ((generate_pictures_ || generate_video_) && want_events) dump_frame(log.size);   // dvs_flow.h:256-335
         if (accumulate) {                                     // dvs_flow.h:341-346: oldest -> newest copy
             LinearEventCloudTemplate<Event> cur;
             cur.reserve(ev_buffer.size());
@@ -422,6 +444,74 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::run_pending() {
         }
     }
     pending_.clear();
+}
+
+// dvs_flow.h:256-335: the frame the reference writes after every slice when pictures / video are requested.
+//   top    : projection_img(ev_buffer, 3, show_final = true)  | mean-timestamp image of the events as recorded
+//   bottom : projection_img(ev_buffer, 3, show_final = false) | mean-timestamp image of the warped events
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::dump_frame(size_t n_slice) {
+    const int S = 3;
+    const int rows = (int)RES_X * S, cols = (int)RES_Y * S;
+    const int n = (int)n_slice;
+    std::vector<double> px((size_t)n), py((size_t)n), fx((size_t)n), fy((size_t)n);
+    std::vector<int32_t> tl((size_t)n);
+    std::vector<uint8_t> nz((size_t)n);
+    int i = 0;
+    for (auto &e : ev_buffer) {
+        px[(size_t)i] = e.pr_x; py[(size_t)i] = e.pr_y; fx[(size_t)i] = (double)e.fr_x; fy[(size_t)i] = (double)e.fr_y;
+        tl[(size_t)i] = (int32_t)e.t; nz[(size_t)i] = e.noise ? 1 : 0;
+        ++i;
+    }
+    bf_ctx *ctx = CudaDriver::context(n, 1, std::max(scale, S));
+    std::vector<uint8_t> pr_t((size_t)rows * cols), pr_f((size_t)rows * cols);
+    std::vector<float> tm_t((size_t)rows * cols), tm_f((size_t)rows * cols);
+    auto check = [](int rc, const char *what) {
+        if (rc < 0) { std::cerr << what << " failed: " << bf_last_error() << std::endl; std::exit(1); }
+    };
+    check(bf_projection_img(ctx, n, fx.data(), fy.data(), nz.data(), S, pr_t.data(), nullptr), "bf_projection_img");
+    check(bf_projection_img(ctx, n, px.data(), py.data(), nz.data(), S, pr_f.data(), nullptr), "bf_projection_img");
+    // time images over the full frame: w = S * RES_X - S so that the image is rows x cols; shift = S / 2
+    check(bf_time_img(ctx, n, fx.data(), fy.data(), tl.data(), nz.data(), rows - S, cols - S, S, S / 2, S / 2, tm_t.data()), "bf_time_img");
+    check(bf_time_img(ctx, n, px.data(), py.data(), tl.data(), nz.data(), rows - S, cols - S, S, S / 2, S / 2, tm_f.data()), "bf_time_img");
+    auto to_u8 = [&](const std::vector<float> &t, std::vector<uint8_t> &o) {
+        float mx = 0;
+        for (float v : t) mx = std::max(mx, v);
+        o.resize(t.size());
+        for (size_t k = 0; k < t.size(); ++k) o[k] = mx > 0 ? (uint8_t)std::min(255.0f, std::max(0.0f, t[k] / mx * 255.0f + 0.5f)) : 0;
+    };
+    std::vector<uint8_t> g_t, g_f;
+    to_u8(tm_t, g_t); to_u8(tm_f, g_f);
+    std::vector<uint8_t> frame((size_t)4 * rows * cols);
+    for (int r = 0; r < rows; ++r) {
+        memcpy(&frame[(size_t)r * 2 * cols], &pr_t[(size_t)r * cols], (size_t)cols);
+        memcpy(&frame[(size_t)r * 2 * cols + cols], &g_t[(size_t)r * cols], (size_t)cols);
+        memcpy(&frame[(size_t)(rows + r) * 2 * cols], &pr_f[(size_t)r * cols], (size_t)cols);
+        memcpy(&frame[(size_t)(rows + r) * 2 * cols + cols], &g_f[(size_t)r * cols], (size_t)cols);
+    }
+    if (generate_pictures_) {
+        const std::string base = img_prefix_ + "/frame_" + std::to_string(frame_count_);
+        std::ofstream pgm(base + ".pgm", std::ofstream::binary);
+        pgm << "P5\n" << 2 * cols << " " << 2 * rows << "\n255\n";
+        pgm.write(reinterpret_cast<const char *>(frame.data()), (std::streamsize)frame.size());
+        // the text the reference renders into the frame (dvs_flow.h:274-318)
+        std::ofstream txt(base + ".txt");
+        txt << "timestamp: " << double(current_slice_time) / 1000000000.0 << "\n"
+            << "%realtime: " << double(on_time_change) / double(time_diff) << "\n"
+            << "Time diff (new): " << double(time_diff) / 1000000000.0 << "\n"
+            << "Events: " << ev_buffer.size() << "\n"
+            << "New events: " << event_diff << "\n"
+            << "Model:\n" << last_model << "\n";
+        frame_count_++;
+    }
+    if (generate_video_) {
+        if (!video_out_) {
+            video_out_.reset(new std::ofstream(video_name_, std::ofstream::binary));
+            if (!*video_out_) std::cout << "Could not open the output video for write" << std::endl;
+            *video_out_ << "YUV4MPEG2 W" << 2 * cols << " H" << 2 * rows << " F" << video_fps_ << ":1 Ip A1:1 Cmono\n";
+        }
+        *video_out_ << "FRAME\n";
+        video_out_->write(reinterpret_cast<const char *>(frame.data()), (std::streamsize)frame.size());
+    }
 }
 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::flush() {

@@ -51,6 +51,11 @@ public:
     }
     bool operator!=(const Event &rhs) const { return !(*this == rhs); }
 
+    // what identifies an event (everything else is per-slice state that Event::reset / the optimiser rewrite)
+    void copy_header_to(Event &o) const {
+        o.fr_x = fr_x; o.fr_y = fr_y; o.t = t; o.timestamp = timestamp; o.noise = noise; o.valid = valid;
+    }
+
     uint get_x() const { return fr_x; }
     uint get_y() const { return fr_y; }
 

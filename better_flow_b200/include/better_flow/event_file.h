@@ -284,6 +284,23 @@ public:
         std::cout << "Read " << cnt << " events, finished" << std::endl << std::flush;
     }
 
+    // The binary format as it lies in the file (16 bytes per event), for callers that build their Events on the fly
+    // instead of materialising a cloud of 152-byte records first.
+    struct BinaryRecord { uint64_t t_ns; uint16_t x, y; uint32_t p; };
+    static std::vector<BinaryRecord> read_binary_records(std::string fname) {
+        static_assert(sizeof(BinaryRecord) == 16, "binary event record is 16 bytes");
+        std::cout << "Reading from file... (" << fname << ")" << std::endl << std::flush;
+        std::vector<BinaryRecord> recs;
+        std::ifstream in(fname, std::ifstream::in | std::ifstream::binary | std::ifstream::ate);
+        if (!in) return recs;
+        const std::streamoff bytes = in.tellg();
+        in.seekg(0);
+        recs.resize(size_t(bytes) / sizeof(BinaryRecord));
+        in.read(reinterpret_cast<char *>(recs.data()), (std::streamsize)(recs.size() * sizeof(BinaryRecord)));
+        std::cout << "Read " << recs.size() << " events, finished" << std::endl << std::flush;
+        return recs;
+    }
+
     // "t x y 1 v u" per event, fixed 9 decimals; x/y and u/v are swapped back to file convention
     template <class T> static void to_file_uv(T *events, std::string fname) {
         std::cout << "Writing events and flow to file... (" << fname << ")" << std::endl << std::flush;

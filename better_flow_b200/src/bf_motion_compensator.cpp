@@ -56,9 +56,9 @@ static void usage(int ret) {
     printf("    [-i/--interactive]\tEnable interactive mode (ignored: GUI feature)\n");
     printf("    [-G]\t\t\t\tUse GPU support (always on: the CUDA back-end is the only implementation)\n");
     printf("    [--stm-disable]\t\t\t\tDo not use previous estimate as a starting point for a new estimate\n");
-    printf("    [--img]\t\t\t\tOutput flow images after every iteration (ignored: visualisation)\n");
+    printf("    [--img]\t\t\t\tOutput flow images after every iteration (frame_N.pgm + frame_N.txt)\n");
     printf("    [--img-prefix <name>]\t\t\t\tSpecify prefix for the generated image files (default = %s)\n", img_prefix.c_str());
-    printf("    [--video]\t\t\t\tOutput a video with flow frames (ignored: visualisation)\n");
+    printf("    [--video]\t\t\t\tOutput a video with flow frames (uncompressed YUV4MPEG2, mono)\n");
     printf("    [--video-name <name>]\t\t\t\tSpecify the name of the video file (default = %s)\n", video_name.c_str());
     printf("    [--video-fps=<value>]\t\t\t\tSpecify video framerate (default = %i)\n", video_fps);
     printf("    [--bufferize-file]\t\t\t\tRead input file to the buffer first (useful for performance testing)\n");
@@ -157,7 +157,9 @@ int main(int argc, char *argv[]) {
     DVS_flow<EVENT_WIDTH, FROM_SEC(TIME_WIDTH)> estimator(event_refresh, FROM_SEC(time_refresh), 0, (size_t)max_events,
                                                           (sll)FROM_SEC(slice_time));
     if (outFileName != NULL) estimator.set_accumulate();
-    else {
+    else if (img || video) {
+        // frames are made from the per-event warped positions: keep reading them back
+    } else {
         estimator.set_lazy_events(true);    // nothing reads the per-event flow: skip its read-back (the per-slice models are unaffected)
         estimator.set_device_ring(device_ring);
     }
@@ -187,24 +189,34 @@ int main(int argc, char *argv[]) {
     if (binary) bufferize_file = true;   // binary input is always read up front
     if (bufferize_file) {
         LinearEventCloud ec;
-        if (binary) EventFile::from_binary(&ec, file);
+        std::vector<EventFile::BinaryRecord> recs;   // binary input stays in its 16-byte records; Events are built on the fly
+        if (binary) recs = EventFile::read_binary_records(file);
         else EventFile::from_file(&ec, file);
+        const ull n_total = binary ? (ull)recs.size() : (ull)ec.size();
 
         clock_t begin = std::clock();
         clock_t begin_slice = std::clock();
         const auto proc0 = std::chrono::steady_clock::now();
         ull i = 0;
-        for (auto &e : ec) {
+        auto feed = [&](Event &e) {
             ++i;
             bool processed = estimator.add_event(e);
             if (processed) {
                 clock_t end_slice = std::clock();
-                std::cout << float(i * 100) / float(ec.size()) << " %\t" << i << "\t"
+                std::cout << float(i * 100) / float(n_total) << " %\t" << i << "\t"
                           << (double(end_slice - begin_slice) / CLOCKS_PER_SEC) << " sec\t" << estimator.get_buf_size()
                           << " events\t" << double(estimator.get_time_diff()) / 1000000000.0 << " slice_td\t"
                           << double(estimator.get_buf_time_diff()) / 1000000000.0 << " buffer_td\n";
                 begin_slice = std::clock();
             }
+        };
+        if (binary) {
+            for (const auto &r : recs) {
+                Event e(r.y, r.x, ull(r.t_ns));
+                feed(e);
+            }
+        } else {
+            for (auto &e : ec) feed(e);
         }
         clock_t end = std::clock();
         std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;

@@ -252,6 +252,19 @@ int bf_multi_locate(bf_multi *m, int slice, bf_ctx **ctx, int *slot, int *device
 long long bf_multi_launch_count(bf_multi *m);
 
 
+/* ---- debug images ----------------------------------------------------------------------------------
+ * EventFile::projection_img (event_file.h:460-515): the "motion-compensated event image" the reference dumps with
+ * --img / --video (dvs_flow.h:256-260) and publishes from its ROS node.  Per non-noise event: x = int(pr_x * scale),
+ * y = int(pr_y * scale) (C truncation), rejected unless 0 <= x < scale * (RES_X - 1) and likewise y (:486-487); a
+ * saturating 8-bit count is splatted on the scale x scale block centred on (x + scale/2, y + scale/2) (:489-501; with
+ * those bounds the block never leaves the image, so the clamps of :494-495 never bite); cv::GaussianBlur(scale x scale)
+ * (:504-506); then the image is scaled by 127 / nonzero_average (event_file.cpp:282-294) with cv::convertScaleAbs
+ * (:508-509).  out = [RES_X * scale][RES_Y * scale] bytes, row-major; *nz_avg (nullable) receives the nonzero average
+ * of the blurred count image.  Pass pr_x / pr_y for the warped image, the events' fr_x / fr_y for show_final = true.
+ * An image without any event is returned all-zero (the reference divides by zero there). */
+int bf_projection_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const uint8_t *noise, int scale,
+                      uint8_t *out, double *nz_avg);
+
 /* ---- device-resident slice ring: DVS_flow's default mode ---------------------------------------
  * Replaces, for the reference's default operating mode (overlapping 50 k-event / 200 ms windows re-minimised every
  * 20 k events / 33 ms, each warm-started from the previous model), the per-slice hand-over of

@@ -209,6 +209,7 @@ bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
 void bf_ring_destroy(bf_ring *r) { delete r; }
 long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
 int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
+    if (g_null) { r->pushed += n; g_ring_pushes += n; return BF_OK; }   // host-overhead timing
     for (int i = 0; i < n; ++i) {
         if (ev[i].fr_x >= r->c->rows || (ev[i].fr_y & 0x7fffu) >= r->c->cols) { g_err = "event outside the sensor"; return BF_ERR_ARG; }
         r->ring[(size_t)(r->pushed % r->cap)] = ev[i];
@@ -219,6 +220,13 @@ int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
 }
 int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain) {
     if (n < 0 || n > r->cap || n > r->pushed) { g_err = "bf_ring_slice: n exceeds the ring's content"; return BF_ERR_ARG; }
+    if (g_null) {                          // host-overhead timing: no gather, no compute
+        const int ticket = r->next_ticket++;
+        memset(&r->res[(size_t)(ticket % r->max_pending)], 0, sizeof(bf_slice_result));
+        r->res[(size_t)(ticket % r->max_pending)].n_events = n;
+        g_ring_slices += 1;
+        return ticket;
+    }
     MockSlice s;
     s.fx.resize(n); s.fy.resize(n); s.t.resize(n); s.noise.resize(n);
     const bool prev_noise = r->have_prev && (r->prev.flags & BF_FLAG_ALL_NOISE);
@@ -248,6 +256,7 @@ int bf_ring_sync(bf_ring *) { return BF_OK; }
 // entry points the mirror references but these tests never reach
 static int unavailable(const char *what) { g_err = std::string(what) + ": not part of the CPU test double"; return BF_ERR_STATE; }
 int bf_time_img(bf_ctx *, int, const double *, const double *, const int32_t *, const uint8_t *, int, int, int, int, int, float *) { return unavailable("bf_time_img"); }
+int bf_projection_img(bf_ctx *, int, const double *, const double *, const uint8_t *, int, uint8_t *, double *) { return unavailable("bf_projection_img"); }
 int bf_project(bf_ctx *, int, const uint16_t *, const uint16_t *, const int32_t *, double *, double *, double *, double *, double, double, double, double, double, double) { return unavailable("bf_project"); }
 int bf_model_from_image(bf_ctx *, int, int, const float *, double *, float *, float *) { return unavailable("bf_model_from_image"); }
 int bf_multi_owner(int slice, int n_devices, int block) { return (n_devices <= 0 || block <= 0 || slice < 0) ? -1 : (slice / block) % n_devices; }

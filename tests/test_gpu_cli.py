@@ -196,3 +196,35 @@ def test_warm_start_chain_slice_by_slice_against_reference(ctx240, oracle_port):
     with open(os.path.join(ROOT, "gpurun_out", "chain_deviation.json"), "w") as f:
         import json
         json.dump(out, f)
+
+
+def test_cli_img_and_video_frames(cli, tmp_path, ctx240):
+    """--img / --video (dvs_flow.h:256-335): one 2 x 2 frame per slice -- projection_img of the events as recorded and
+    as warped (EventFile::projection_img on the device) beside the mean-timestamp images -- as PGM + overlay text, and
+    as an uncompressed YUV4MPEG2 stream."""
+    from helpers import ring_slice
+    st = synth.make_stream(240, 180, 1.0e6, 0.05, seed=61)
+    binf = tmp_path / "s.bin"
+    write_bin(binf, st)
+    vid = tmp_path / "out.y4m"
+    r = run([cli, "--quiet", "--max-iter=6", "--img", "--img-prefix", str(tmp_path), "--video", "--video-name", str(vid),
+             "--flow-out=%s" % (tmp_path / "flow.txt"), str(binf)])
+    assert r.returncode == 0, r.stderr[-1500:]
+    n_slices = len(open(tmp_path / "flow.txt").read().splitlines())
+    assert n_slices >= 2
+    rows, cols = 180 * 3, 240 * 3
+    for k in range(n_slices):
+        raw = open(tmp_path / ("frame_%d.pgm" % k), "rb").read()
+        head = b"P5\n%d %d\n255\n" % (2 * cols, 2 * rows)
+        assert raw.startswith(head) and len(raw) == len(head) + 4 * rows * cols
+        txt = open(tmp_path / ("frame_%d.txt" % k)).read()
+        assert "timestamp:" in txt and "New events:" in txt and "Shift" in txt
+    frame0 = np.frombuffer(open(tmp_path / "frame_0.pgm", "rb").read()[len(head):], dtype=np.uint8).reshape(2 * rows, 2 * cols)
+    # slice 0 = the first 20000 events; the top-left panel is projection_img of them as recorded (show_final = true)
+    idx, _ = ring_slice(st.t_ns, 20000)
+    want, _ = ctx240.projection_img(st.y[idx].astype(np.float64), st.x[idx].astype(np.float64), 3)
+    assert np.array_equal(frame0[:rows, :cols], want)
+    assert frame0[rows:, :cols].any() and frame0[:rows, cols:].any() and frame0[rows:, cols:].any()
+    assert not np.array_equal(frame0[rows:, :cols], frame0[:rows, :cols])        # the warped image differs from the raw one
+    y4m = open(vid, "rb").read()
+    assert y4m.startswith(b"YUV4MPEG2 W%d H%d F30:1" % (2 * cols, 2 * rows)) and y4m.count(b"FRAME\n") >= n_slices

@@ -300,3 +300,20 @@ def test_permutation_invariance_bit_exact(ctx240):
     perm = np.random.default_rng(2).permutation(len(sl.fr_x))
     b = ctx240.minimize(sl.fr_x[perm], sl.fr_y[perm], sl.t_ns[perm], max_iter=8)
     assert a["iters"] == b["iters"] and np.array_equal(a["model"], b["model"])
+
+
+@pytest.mark.parametrize("scale", [1, 3, 5])
+def test_projection_img_equals_opencv_golden(ctx240, scale):
+    """bf_projection_img (EventFile::projection_img, event_file.h:460-515: the reference's --img / ROS debug image) against
+    fixtures minted with the REAL cv2.GaussianBlur / cv2.convertScaleAbs (oracle/make_golden_img.py): byte-identical."""
+    import os
+    from oracle import make_golden_img as mg
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "projection_img.npz"))
+    for name, (px, py, nz) in mg.cases().items():
+        assert np.array_equal(G[name + "_input_checksum"], [float(np.sum(px * 3 + py)), float(nz.sum())])   # same inputs as the fixture
+        img, avg = ctx240.projection_img(px, py, scale, noise=nz)
+        want = G["%s_s%d" % (name, scale)]
+        assert img.shape == want.shape and avg == G["%s_s%d_avg" % (name, scale)][0]
+        assert np.array_equal(img, want), (name, scale, int(np.sum(img != want)))
+    empty, avg = ctx240.projection_img(np.zeros(0), np.zeros(0), scale)
+    assert avg == 0 and not empty.any()
