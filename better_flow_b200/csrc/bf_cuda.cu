@@ -256,7 +256,7 @@ __device__ void run_slice_local(const KParams &P, Smem &S, GroupWs *ws, unsigned
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
     short2 *col_tab = reinterpret_cast<short2 *>(row_tab + P.tab_rows);
     unsigned *bm = reinterpret_cast<unsigned *>(col_tab + P.tab_cols);
-    fill_cell_tables<SH>(row_tab, col_tab, S.g.rows, S.g.cols, 2 * SH);
+    fill_cell_tables<SH, true>(row_tab, col_tab, S.g.rows, S.g.cols, 2 * SH);
     if (threadIdx.x == 0) local_opt_init(S.lopt, S.g.scale);
     __syncthreads();
     int buf = 0;
@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
 
         if (guard == 0 && S.sd.mode == 1) {
             if (S.sd.scale == 1) run_slice_local<0>(P, S, ws, bar_target, tag, group, rank);
-            else run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
+            else if (S.sd.scale == 3) run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
+            else run_slice_local<2>(P, S, ws, bar_target, tag, group, rank);
         } else if (guard == 0) {
             switch (S.sd.scale) {
                 case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank, &TM); break;
@@ -1253,7 +1254,7 @@ int bf_batch_add(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const in
 // OptimizerLocal(LinearEventCloud*, scale) (optimizer_sampler.h:41-56): the slice is minimised by
 // OptimizerLocal::run instead of OptimizerRolling::run.
 int bf_batch_add_local(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, const int32_t *t_ns, int n, int scale) {
-    if (scale != 1 && scale != 3) return fail(BF_ERR_ARG, "bf_batch_add_local: scale %d unsupported (1 or 3)", scale);
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "bf_batch_add_local: scale %d unsupported (1, 3 or 5)", scale);
     const int slot = bf_batch_add(c, fr_x, fr_y, t_ns, nullptr, n, scale, -1, nullptr);
     if (slot >= 0) c->h_slices[slot].mode = 1;
     return slot;
@@ -1261,7 +1262,6 @@ int bf_batch_add_local(bf_ctx *c, const uint16_t *fr_x, const uint16_t *fr_y, co
 
 int bf_batch_slot_mode(bf_ctx *c, int slot, int mode) {
     if (!c || slot < 0 || slot >= c->n_slices || (mode != 0 && mode != 1)) return fail(BF_ERR_ARG, "bf_batch_slot_mode: bad arguments");
-    if (mode == 1 && c->h_slices[slot].scale > 3) return fail(BF_ERR_ARG, "OptimizerLocal mode supports scale 1 or 3");
     c->h_slices[slot].mode = mode;
     c->uploaded = c->ran = false;
     return BF_OK;

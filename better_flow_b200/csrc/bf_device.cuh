@@ -55,13 +55,16 @@ typedef unsigned long long u64;
 // The image pass works on CELLS: 8 output rows x (32 - 2H) output columns, H = scale/2 + 1 being the
 // halo needed by the box sum (scale/2) plus the 3x3 Scharr (1).  A warp owns a cell: lane l holds
 // column l of the (8 + 2H) x 32 point patch in registers, so horizontal neighbours are shuffles.
-template <int SH> struct CellCfg {
-    static constexpr int H = SH + 1;
+// OptimizerLocal's image is the box-summed count image followed by a (2 SH + 1)^2 Gaussian blur: its halo is the box
+// radius plus the blur radius, 2 SH, which exceeds SH + 1 at scale 5 only -- LOCAL selects that geometry (H = 4, 24
+// output columns per cell) for the slices minimised by OptimizerLocal at scale 5; every other case is unchanged.
+template <int SH, bool LOCAL = false> struct CellCfg {
+    static constexpr int H = (LOCAL && 2 * SH > SH + 1) ? 2 * SH : SH + 1;
     static constexpr int PR = BF_CELL_ROWS + 2 * H;   // patch rows held per lane
     static constexpr int AR = BF_CELL_ROWS + 2;       // mean-time rows (1-row halo for Scharr)
     static constexpr int CW = 32 - 2 * H;             // output columns per cell
 };
-#define BF_CW_MIN 26   // CellCfg<2>::CW, for sizing the flag array
+#define BF_CW_MIN 24   // CellCfg<2, true>::CW (the narrowest cell), for sizing the flag array
 
 struct SliceDesc {
     long long ev_off;   // first event of the slice in the batch arrays
@@ -374,9 +377,9 @@ __device__ __forceinline__ void mark_cells(unsigned *flags, unsigned tag, int x,
 // box radius SH of it -- so the neighbour cell is stamped for events within SH of the border, not within
 // the patch halo H = SH + 1 (the halo is what the cell READS, not what makes it live).  OptimizerLocal's
 // blur spreads one more box radius: margin 2 * SH.
-template <int SH>
+template <int SH, bool LOCAL = false>
 __device__ __forceinline__ void fill_cell_tables(int2 *row_tab, short2 *col_tab, int rows, int cols, int margin) {
-    typedef CellCfg<SH> C;
+    typedef CellCfg<SH, LOCAL> C;
     const int n_ci = (rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (cols + C::CW - 1) / C::CW;
     for (int x = threadIdx.x; x < rows; x += blockDim.x) {
         const int ci = x >> 3, lx = x & 7;
@@ -834,9 +837,9 @@ __device__ __forceinline__ int compact_cells(const unsigned *flags, unsigned tag
 }
 
 // Zero the 8 x CW interior of one cell with coalesced row stores (one warp).
-template <int SH>
+template <int SH, bool LOCAL = false>
 __device__ __forceinline__ void cell_clear(u64 *img, int pitch, int ci, int cj) {
-    typedef CellCfg<SH> C;
+    typedef CellCfg<SH, LOCAL> C;
     const int lane = threadIdx.x & 31;
     if (lane < C::CW) {
         u64 *p = img + (long long)(ci * BF_CELL_ROWS + BF_BORDER) * pitch + (cj * C::CW + BF_BORDER + lane);
@@ -865,7 +868,7 @@ __device__ BF_PASS_INLINE int image_pass(Acc &acc, const u64 *img, int pitch, co
                           int *scan, float *out_img, float *out_gx, float *out_gy, u64 *img_clear,
                           const unsigned *flags_clear, unsigned tag_clear, const unsigned short *list_prev,
                           int n_prev, TmaWarp *tma = nullptr) {
-    typedef CellCfg<SH> C;
+    typedef CellCfg<SH, MODE == 1> C;
     const int n_ci = (g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS, n_cj = (g.cols + C::CW - 1) / C::CW;
     const int n_cells = n_ci * n_cj;
     const int i0 = g.rows / 2, j0 = g.cols / 2;
@@ -885,7 +888,7 @@ __device__ BF_PASS_INLINE int image_pass(Acc &acc, const u64 *img, int pitch, co
             if (k0 < 0) k0 += n_warps;
             for (int k = k0; k < total; k += n_warps) {
                 const int c = base + (int)list[k];
-                cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
+                cell_clear<SH, MODE == 1>(img_clear, pitch, c / n_cj, c % n_cj);
             }
             dealt_clear = (dealt_clear + total) % n_warps;
         }
@@ -946,7 +949,7 @@ __device__ BF_PASS_INLINE int image_pass(Acc &acc, const u64 *img, int pitch, co
     if (img_clear != nullptr && one_chunk && list_prev != nullptr) {
         for (int k = rank * BF_NW + warp; k < n_prev; k += G * BF_NW) {
             const int c = (int)list_prev[k];
-            cell_clear<SH>(img_clear, pitch, c / n_cj, c % n_cj);
+            cell_clear<SH, MODE == 1>(img_clear, pitch, c / n_cj, c % n_cj);
         }
     }
     return n_live;
@@ -965,11 +968,63 @@ __device__ BF_PASS_INLINE int image_pass(Acc &acc, const u64 *img, int pitch, co
 //   blur         B = cv::GaussianBlur(C, Size(s, s), 0, 0) on CV_8UC1 = binomial [1 2 1]/4 per axis in fixed
 //                    point, i.e. (sum + 8) >> 4 for s = 3, BORDER_REFLECT_101 at the image edges; s = 1: B = C;
 //   score sums   number and sum of the non-zero B (get_event_score, :192-204) -> acc.cnt, acc.si.
+//   scale 5: the same with a 5 x 5 box and the binomial [1 4 6 4 1]/16 per axis, (sum + 128) >> 8, on the LOCAL cell
+//   geometry (halo 4 = box radius 2 + blur radius 2: 16 patch rows, 24 output columns).
+__device__ __forceinline__ void local_cell_process_s5(Acc &acc, const u64 *img, int pitch, const BfPack &pk, int ci, int cj,
+                                                      int rows, int cols) {
+    typedef CellCfg<2, true> C;     // H = 4, PR = 16, CW = 24
+    constexpr int NC = BF_CELL_ROWS + 4;   // count rows: image rows ci*8 - 2 .. ci*8 + 9
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const u64 *p = img + (long long)(ci * BF_CELL_ROWS - C::H + BF_BORDER) * pitch + (cj * C::CW - C::H + BF_BORDER + lane);
+    unsigned pc[C::PR];             // point counts of the patch column (the time sums are not needed here)
+#pragma unroll
+    for (int r = 0; r < C::PR; ++r) pc[r] = (unsigned)(__ldcg(p + (long long)r * pitch) >> 32) >> (pk.cnt_shift - 32);
+    int Cn[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const unsigned v = pc[k] + pc[k + 1] + pc[k + 2] + pc[k + 3] + pc[k + 4];      // patch rows k .. k+4 <-> image rows centred on count row k
+        unsigned a = v;
+        a += __shfl_up_sync(FULL, v, 1); a += __shfl_down_sync(FULL, v, 1);
+        a += __shfl_up_sync(FULL, v, 2); a += __shfl_down_sync(FULL, v, 2);
+        Cn[k] = (int)min(a, 255u);
+    }
+    // BORDER_REFLECT_101 rows: image row -1 := 1, -2 := 2; row `rows` := rows - 2, rows + 1 := rows - 3
+    if (ci == 0) { Cn[1] = Cn[3]; Cn[0] = Cn[4]; }
+#pragma unroll
+    for (int k = 2; k < NC; ++k) {
+        const int ir = ci * BF_CELL_ROWS - 2 + k;
+        if (ir == rows) Cn[k] = Cn[k - 2];
+        else if (ir == rows + 1 && k >= 4) Cn[k] = Cn[k - 4];
+    }
+    const int j = cj * C::CW + lane - C::H;
+    const bool out_lane = (lane >= C::H) && (lane < 32 - C::H) && j < cols;
+    int n_nz = 0, s_nz = 0;
+#pragma unroll
+    for (int r = 0; r < BF_CELL_ROWS; ++r) {
+        const int i = ci * BF_CELL_ROWS + r;
+        const int V = Cn[r] + 4 * Cn[r + 1] + 6 * Cn[r + 2] + 4 * Cn[r + 3] + Cn[r + 4];    // count rows i-2 .. i+2
+        int L1 = __shfl_up_sync(FULL, V, 1), R1 = __shfl_down_sync(FULL, V, 1);
+        int L2 = __shfl_up_sync(FULL, V, 2), R2 = __shfl_down_sync(FULL, V, 2);
+        if (j == 0) { L1 = R1; L2 = R2; }              // columns -1, -2 := 1, 2
+        else if (j == 1) L2 = V;                        // column -1 := 1
+        if (j == cols - 1) { R1 = L1; R2 = L2; }        // columns cols, cols + 1 := cols - 2, cols - 3
+        else if (j == cols - 2) R2 = V;                 // column cols := cols - 2
+        const int B = (L2 + 4 * L1 + 6 * V + 4 * R1 + R2 + 128) >> 8;
+        if (out_lane && i < rows && B > 0) { n_nz += 1; s_nz += B; }
+    }
+    acc.cnt += n_nz;
+    acc.si += s_nz;
+}
+
 template <int SH>
 __device__ __forceinline__ void local_cell_process(Acc &acc, const u64 *img, int pitch, const BfPack &pk, int ci, int cj,
                                                    int rows, int cols) {
+    if constexpr (SH == 2) {
+        local_cell_process_s5(acc, img, pitch, pk, ci, cj, rows, cols);
+        return;
+    }
     typedef CellCfg<SH> C;
-    static_assert(SH <= 1, "OptimizerLocal on the device supports scale 1 and 3 (scale 5 needs a 4-pixel halo)");
     const int lane = threadIdx.x & 31;
     const u64 *p = img + (long long)(ci * BF_CELL_ROWS - C::H + BF_BORDER) * pitch + (cj * C::CW - C::H + BF_BORDER + lane);
     u64 P[C::PR];
@@ -1099,7 +1154,7 @@ __device__ void local_event_pass(const KParams &P, const SliceDesc &sd, const Bf
         }
     }
     {
-        typedef CellCfg<SH> C;
+        typedef CellCfg<SH, true> C;
         flush_stamp_bitmap(bm, flags, tag, ((g.rows + BF_CELL_ROWS - 1) / BF_CELL_ROWS) * ((g.cols + C::CW - 1) / C::CW));
     }
 }

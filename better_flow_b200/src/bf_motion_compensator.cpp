@@ -172,7 +172,6 @@ int main(int argc, char *argv[]) {
     estimator.set_batch(batch);
     estimator.set_gpus(gpus);
     if (optimizer_local) {
-        if (scale > 3) { fprintf(stderr, "--optimizer=local supports --scale=1 or 3.\n"); return 1; }
         estimator.set_optimizer_local(true);
     }
     estimator.set_quiet(quiet);

@@ -181,7 +181,7 @@ int bf_minimize(bf_ctx *ctx, const uint16_t *fr_x, const uint16_t *fr_y, const i
  * Gaussian-blurred (scale x scale) and scored by the mean of its non-zero pixels; nx, ny are moved
  * alternately by +-dn, dn halving and flipping whenever the score does not improve, until
  * hypot(dnx, dny) <= dn_th.  Runs in the same persistent launch as the rolling slices of a batch.
- * t_ns is Event::t as the caller has it (the class never calls set_local_time).  scale: 1 or 3.
+ * t_ns is Event::t as the caller has it (the class never calls set_local_time).  scale: 1, 3 or 5.
  * Result record (bf_slice_result) of such a slice:
  *   model.total_dx = nx, model.total_dy = ny      (get_nx / get_ny)
  *   model.dx = last_score, model.dy = dnx, model.rot = dny, model.div = dn_th

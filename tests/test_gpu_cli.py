@@ -207,7 +207,7 @@ def test_cli_img_and_video_frames(cli, tmp_path, ctx240):
     binf = tmp_path / "s.bin"
     write_bin(binf, st)
     vid = tmp_path / "out.y4m"
-    r = run([cli, "--quiet", "--max-iter=6", "--img", "--img-prefix", str(tmp_path), "--video", "--video-name", str(vid),
+    r = run([cli, "--quiet", "--max-iter=6", "--img", "--img-prefix", str(tmp_path), "--video", "--video-name", str(vid), "--video-fps=30",
              "--flow-out=%s" % (tmp_path / "flow.txt"), str(binf)])
     assert r.returncode == 0, r.stderr[-1500:]
     n_slices = len(open(tmp_path / "flow.txt").read().splitlines())

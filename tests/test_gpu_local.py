@@ -84,9 +84,44 @@ def test_mixed_batch_rolling_and_local_slices(ctx240, oracle_port):
             assert r["iters"] == want["iters"] and r["model"].tobytes() == want["model"].tobytes()
 
 
-def test_local_rejects_scale5(ctx240):
-    with pytest.raises(bf.BfError):
-        ctx240.add_local(np.zeros(10, np.uint16), np.zeros(10, np.uint16), np.zeros(10, np.int32), 5)
+def test_local_scale5_equals_oracle(ctx240, oracle_port):
+    """OptimizerLocal at scale 5 (optimizer_sampler.cpp:124-149 with a 5 x 5 splat and cv::GaussianBlur(5 x 5)): the
+    cell geometry with a 4-pixel halo.  Exact equality with the oracle (itself bit-equal to the compiled reference
+    class at scale 5, tests/test_oracle_local.py), for several CTA groupings, plus a window that touches all four
+    image borders (the reflect-101 fix-ups of the blur) and a mixed batch."""
+    cases = [(74, (40.0, -20.0), 0.02), (75, (-70.0, 30.0), 0.03)]
+    for seed, vel, dur in cases:
+        st = synth.make_stream(240, 180, 1.5e6, dur, seed=seed, vel=vel)
+        sl = synth.cut_slices(st, dur)[0]
+        want = oracle_port.local_minimize(sl.fr_x, sl.fr_y, sl.t_ns, 5, want_image=True)
+        for G in (0, 1, 5):
+            ctx240.set_option("group_size", G)
+            got = ctx240.local_minimize(sl.fr_x, sl.fr_y, sl.t_ns, 5)
+            check(got, [want[k] for k in ("nx", "ny", "score", "dnx", "dny", "dn_th")], want["rc"], want["steps"],
+                  int((want["image"] > 0).sum()))
+    ctx240.set_option("group_size", 0)
+    # a small dense window: every border row / column of the image carries events
+    rng = np.random.default_rng(8)
+    n = 30000
+    fx = rng.integers(60, 101, n).astype(np.uint16); fy = rng.integers(90, 151, n).astype(np.uint16)
+    t = np.sort(rng.integers(0, 20_000_000, n)).astype(np.int32)[::-1].copy()
+    want = oracle_port.local_minimize(fx, fy, t, 5, want_image=True)
+    got = ctx240.local_minimize(fx, fy, t, 5)
+    check(got, [want[k] for k in ("nx", "ny", "score", "dnx", "dny", "dn_th")], want["rc"], want["steps"], int((want["image"] > 0).sum()))
+    # rolling scale 5, local scale 5 and local scale 3 in one launch
+    st = synth.make_stream(240, 180, 1.5e6, 0.06, seed=76)
+    sls = synth.cut_slices(st, 0.02)[:3]
+    ctx240.reset()
+    ctx240.add(sls[0].fr_x, sls[0].fr_y, sls[0].t_ns, 5, 6)
+    ctx240.add_local(sls[1].fr_x, sls[1].fr_y, sls[1].t_ns, 5)
+    ctx240.add_local(sls[2].fr_x, sls[2].fr_y, sls[2].t_ns, 3)
+    ctx240.run()
+    for k, sc in ((1, 5), (2, 3)):
+        o = oracle_port.local_minimize(sls[k].fr_x, sls[k].fr_y, sls[k].t_ns, sc)
+        g = ctx240.local_view(ctx240.result(k))
+        assert (g["nx"], g["ny"], g["score"], g["steps"]) == (o["nx"], o["ny"], o["score"], o["steps"])
+    ex = oracle_port.minimize(sls[0].fr_x, sls[0].fr_y, sls[0].t_ns, scale=5, max_iter=6, accum_mode=1)
+    assert ctx240.result(0)["iters"] == ex["iters"] and np.allclose(ctx240.result(0)["model"][7:11], ex["model"][7:11], rtol=1e-9, atol=0)
 
 
 def test_cli_optimizer_local(tmp_path, oracle_port):

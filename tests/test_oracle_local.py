@@ -89,7 +89,7 @@ def test_restatement_equals_compiled_reference_on_fresh_clouds(oracle_port):
     from oracle import ref
     if not ref.available():
         pytest.skip("oracle/_ref not present in this snapshot")
-    for seed, vel, dur, scale in [(71, (30.0, 10.0), 0.02, 3), (72, (-90.0, 50.0), 0.04, 3), (73, (60.0, 60.0), 0.04, 1)]:
+    for seed, vel, dur, scale in [(71, (30.0, 10.0), 0.02, 3), (72, (-90.0, 50.0), 0.04, 3), (73, (60.0, 60.0), 0.04, 1), (74, (40.0, -20.0), 0.02, 5)]:
         st = synth.make_stream(240, 180, 1.5e6, dur, seed=seed, vel=vel)
         sl = synth.cut_slices(st, dur)[0]
         a = oracle_port.local_minimize(sl.fr_x, sl.fr_y, sl.t_ns, scale, want_image=True)
