@@ -65,7 +65,7 @@ ABI_SYMBOLS = (
     "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
-    "bf_projection_img",
+    "bf_projection_img", "bf_batch_add_delta", "bf_batch_upload_bytes",
     "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed",
 )
 
@@ -137,6 +137,9 @@ def load() -> C.CDLL:
         lib.bf_multi_locate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.bf_multi_launch_count.argtypes = [C.c_void_p]
         lib.bf_multi_launch_count.restype = C.c_longlong
+        lib.bf_batch_add_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.bf_batch_upload_bytes.argtypes = [C.c_void_p]
+        lib.bf_batch_upload_bytes.restype = C.c_longlong
         lib.bf_projection_img.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.bf_ring_create.restype = C.c_void_p
         lib.bf_ring_create.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
@@ -248,6 +251,17 @@ class Context:
         m = Model.from_array(init) if init is not None else None
         return self._chk(self.lib.bf_batch_add_packed(self.h, _ptr(ev), len(ev), scale, max_iter,
                                                       C.byref(m) if m is not None else None))
+
+    def add_delta(self, events, scale=3, max_iter=-1, init=None):
+        """Queue a slice in the compact 6-byte upload format (raises BfError when it cannot be represented)."""
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        m = Model.from_array(init) if init is not None else None
+        return self._chk(self.lib.bf_batch_add_delta(self.h, _ptr(ev), len(ev), scale, max_iter,
+                                                     C.byref(m) if m is not None else None))
+
+    @property
+    def upload_bytes(self):
+        return int(self.lib.bf_batch_upload_bytes(self.h))
 
     def staging(self) -> np.ndarray:
         cap = C.c_longlong(0)

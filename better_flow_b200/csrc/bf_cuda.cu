@@ -680,6 +680,53 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
     }
 }
 
+// ---- compact upload format: 6-byte delta records -> bf_event (include/bf_cuda.h: bf_batch_add_delta) --------------
+struct DeltaBlock {          // up to 1024 consecutive events of one slice
+    long long first;         // index of the block's first event in the batch arrays
+    int count;
+    int t0;                  // local time of the first event
+};
+#define BF_DELTA_BLOCK 1024
+// One CTA of 256 threads per block, 4 consecutive events per thread: t[i] = t0 - (dt[1] + ... + dt[i]).
+__global__ void __launch_bounds__(256) bf_delta_expand_kernel(const unsigned short *rec, const DeltaBlock *blocks, bf_event *out) {
+    __shared__ unsigned warp_tot[8];
+    const DeltaBlock b = blocks[blockIdx.x];
+    const unsigned short *r = rec + (size_t)b.first * 3;
+    const int i0 = (int)threadIdx.x * 4;
+    unsigned x[4], y[4], dt[4];
+    unsigned run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        unsigned w0 = 0, w1 = 0, w2 = 0;
+        if (i < b.count) { w0 = r[3 * i]; w1 = r[3 * i + 1]; w2 = r[3 * i + 2]; }
+        x[k] = w0 & 0xfffu;
+        y[k] = (w0 >> 12) | ((w1 & 0xffu) << 4) | ((w1 & 0x100u) ? BF_EVENT_NOISE : 0u);
+        run += (w1 >> 9) | (w2 << 7);
+        dt[k] = run;                                 // inclusive sum within the thread
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned before = incl - run;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        if (i < b.count) {
+            bf_event e;
+            e.fr_x = (uint16_t)x[k]; e.fr_y = (uint16_t)y[k]; e.t_ns = b.t0 - (int)(before + dt[k]);
+            out[b.first + i] = e;
+        }
+    }
+}
+
 // ---- EventFile::projection_img (event_file.h:460-515) -------------------------------------------------------------
 // Not a performance path (debug images): four plain per-event / per-pixel kernels.
 __global__ void bf_proj_splat_kernel(int n, const double *pr_x, const double *pr_y, const unsigned char *noise, int scale,
@@ -885,6 +932,13 @@ struct bf_ctx {
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
 
+    // compact upload format (bf_batch_add_delta): 6-byte records + block descriptors, pinned and on the device
+    unsigned short *h_delta = nullptr, *d_delta[2] = {nullptr, nullptr};
+    struct DeltaBlock *h_blocks = nullptr, *d_blocks[2] = {nullptr, nullptr};
+    long long blocks_cap = 0;
+    int n_blocks = 0;
+    int delta_slices = 0;                  // slices of the current batch that were added in delta format
+    std::vector<int> slice_block0;         // first block descriptor of every slice (+ one past the end)
     std::vector<struct bf_ring *> rings;   // device-resident slice rings of this context (destroyed with it)
 
     // batch state
@@ -1136,6 +1190,8 @@ void bf_ctx_destroy(bf_ctx *c) {
     cudaFreeHost(c->h_events); cudaFreeHost(c->h_slices); cudaFreeHost(c->h_results);
     cudaFree(c->ev_buf[0]); cudaFree(c->ev_buf[1]); cudaFree(c->sl_buf[0]); cudaFree(c->sl_buf[1]);
     cudaFree(c->d_state); cudaFree(c->d_pr_out); cudaFree(c->d_nxy);
+    cudaFreeHost(c->h_delta); cudaFree(c->d_delta[0]); cudaFree(c->d_delta[1]);
+    cudaFreeHost(c->h_blocks); cudaFree(c->d_blocks[0]); cudaFree(c->d_blocks[1]);
     cudaFree(c->d_results); cudaFree(c->d_ctrl); cudaFree(c->d_partials); cudaFree(c->d_images); cudaFree(c->d_flags);
     cudaFree(c->d_stage); cudaFree(c->d_prof); cudaFree(c->d_join);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1217,6 +1273,7 @@ int bf_batch_reset(bf_ctx *c) {
     if (!c) return fail(BF_ERR_ARG, "null context");
     c->n_slices = 0; c->n_events = 0;
     c->uploaded = c->ran = c->have_events = false;
+    c->n_blocks = 0; c->delta_slices = 0; c->slice_block0.clear();
     return BF_OK;
 }
 
@@ -1289,6 +1346,57 @@ int bf_batch_add_packed(bf_ctx *c, const bf_event *events, int n, int scale, int
     return slot;
 }
 
+int bf_batch_add_delta(bf_ctx *c, const bf_event *events, int n, int scale, int max_iter, const bf_model *init) {
+    if (!c || n < 0 || (n > 0 && !events)) return fail(BF_ERR_ARG, "bf_batch_add_delta: bad arguments");
+    if (c->n_events + n > c->max_events) return fail(BF_ERR_ARG, "batch event capacity exceeded (%lld)", c->max_events);
+    if (c->delta_slices != c->n_slices) return fail(BF_ERR_STATE, "bf_batch_add_delta: the batch already holds slices in 8-byte format");
+    if (!bf_events_in_sensor(events, n, c->res_x, c->res_y)) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
+    CU(cudaSetDevice(c->device));
+    if (!c->h_delta) {
+        c->blocks_cap = c->max_events / BF_DELTA_BLOCK + c->max_slices + 2;
+        CU(cudaMallocHost(&c->h_delta, (size_t)(c->max_events + 4) * 6));
+        CU(cudaMallocHost(&c->h_blocks, (size_t)c->blocks_cap * sizeof(DeltaBlock)));
+    }
+    const int nb = (n + BF_DELTA_BLOCK - 1) / BF_DELTA_BLOCK;
+    if (c->n_blocks + nb > c->blocks_cap) return fail(BF_ERR_ARG, "bf_batch_add_delta: block table full");
+    unsigned short *rec = c->h_delta + (size_t)c->n_events * 3;
+    for (int i = 0; i < n; ++i) {
+        const bf_event &e = events[i];
+        const unsigned fy = e.fr_y & 0x7fffu, nz = (e.fr_y & BF_EVENT_NOISE) ? 1u : 0u;
+        long long dt = 0;
+        if (i % BF_DELTA_BLOCK != 0) dt = (long long)events[i - 1].t_ns - (long long)e.t_ns;
+        if (e.fr_x >= 4096u || fy >= 4096u || dt < 0 || dt >= (1ll << 23))
+            return fail(BF_ERR_ARG, "bf_batch_add_delta: slice not representable (coordinate >= 4096, time running backwards or a gap >= 8.4 ms)");
+        rec[3 * i] = (unsigned short)(e.fr_x | ((fy & 0xfu) << 12));
+        rec[3 * i + 1] = (unsigned short)((fy >> 4) | (nz << 8) | (((unsigned)dt & 0x7fu) << 9));
+        rec[3 * i + 2] = (unsigned short)((unsigned)dt >> 7);
+    }
+    for (int k = 0; k < nb; ++k) {
+        DeltaBlock &b = c->h_blocks[c->n_blocks + k];
+        b.first = c->n_events + (long long)k * BF_DELTA_BLOCK;
+        b.count = std::min(BF_DELTA_BLOCK, n - k * BF_DELTA_BLOCK);
+        b.t0 = events[(size_t)k * BF_DELTA_BLOCK].t_ns;
+    }
+    // (the 8-byte copy is kept too: bf_batch_upload / bf_batch_run use it, and it is the fall-back of the streamed path)
+    memcpy(c->h_events + c->n_events, events, (size_t)n * sizeof(bf_event));
+    const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
+    if (slot < 0) return slot;
+    c->slice_block0.resize((size_t)slot + 2);
+    c->slice_block0[(size_t)slot] = c->n_blocks;
+    c->n_blocks += nb;
+    c->slice_block0[(size_t)slot + 1] = c->n_blocks;
+    c->n_events += n;
+    c->delta_slices += 1;
+    return slot;
+}
+
+long long bf_batch_upload_bytes(bf_ctx *c) {
+    if (!c) return 0;
+    const long long table = (long long)c->n_slices * (long long)sizeof(SliceDesc);
+    if (c->n_slices > 0 && c->delta_slices == c->n_slices) return c->n_events * 6 + (long long)c->n_blocks * (long long)sizeof(DeltaBlock) + table;
+    return c->n_events * (long long)sizeof(bf_event) + table;
+}
+
 bf_event *bf_batch_staging(bf_ctx *c, long long *capacity) {
     if (!c) return nullptr;
     if (capacity) *capacity = c->max_events;
@@ -1339,9 +1447,38 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
         CU(cudaMemset(c->ev_buf[nb], 0, (size_t)(c->max_events + 2) * sizeof(bf_event)));
         CU(cudaMalloc(&c->sl_buf[nb], (size_t)c->max_slices * sizeof(SliceDesc)));
     }
+    const bool delta = c->delta_slices == c->n_slices && c->h_delta != nullptr;
+    if (delta && !c->d_delta[nb]) {
+        CU(cudaMalloc(&c->d_delta[nb], (size_t)(c->max_events + 4) * 6));
+        CU(cudaMalloc(&c->d_blocks[nb], (size_t)c->blocks_cap * sizeof(DeltaBlock)));
+    }
     unsigned *d_ready = c->d_ready + 64 * nb, *h_ready = c->h_ready + 64 * nb;
     // the copy engine must not write this buffer before the last launch that read it has finished
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[nb], 0));
+    if (delta) {
+        // Compact upload: the 6-byte records and their block table go up on the copy stream -- under the kernel of the
+        // PREVIOUS batch, which reads the other buffer -- and are expanded to bf_event records by one small kernel on the
+        // compute stream right before this batch's launch.  (The expansion cannot be chunk-streamed under the persistent
+        // kernel like the 8-byte copies below: that kernel holds every register of every SM, so a second kernel would
+        // wait for it while it waits for the events -- measured as a hang, round 2.)
+        CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(c->d_delta[nb], c->h_delta, (size_t)c->n_events * 6, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(c->d_blocks[nb], c->h_blocks, (size_t)c->n_blocks * sizeof(DeltaBlock), cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        if (c->n_blocks > 0) {
+            bf_delta_expand_kernel<<<c->n_blocks, 256, 0, c->stream>>>(c->d_delta[nb], c->d_blocks[nb], c->ev_buf[nb]);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        }
+        c->cur = nb;
+        c->d_events = c->ev_buf[nb];
+        c->d_slices = c->sl_buf[nb];
+        c->uploaded = true;
+        const int rc = launch_impl(c, want_events, nullptr);
+        if (rc != BF_OK) return rc;
+        return bf_batch_download(c);
+    }
     CU(cudaMemsetAsync(d_ready, 0, sizeof(unsigned), c->copy_stream));
     CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copy, c->copy_stream));

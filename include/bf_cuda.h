@@ -252,6 +252,21 @@ int bf_multi_locate(bf_multi *m, int slice, bf_ctx **ctx, int *slot, int *device
 long long bf_multi_launch_count(bf_multi *m);
 
 
+/* ---- compact upload format (end-to-end path) ----------------------------------------------------------------------
+ * The 8-byte bf_event is what the kernel reads; over PCIe a slice travels as 6-byte DELTA records: 12-bit fr_x, 12-bit
+ * fr_y, the noise bit and a 23-bit time difference to the previous event of the slice (slices are handed over
+ * newest -> oldest, dvs_flow.h:196-198, so local times decrease: dt = t[i-1] - t[i] >= 0), with an absolute local time
+ * every 1024 events (one 16-byte block descriptor).  bf_batch_add_delta packs a slice into the context's pinned delta
+ * staging; when EVERY slice of a batch was added this way, bf_batch_run_streamed uploads the 6-byte records (25 % fewer
+ * bytes: with 8 GPUs on one host the H2D of 8 x 426 MB per step is what bounds the end-to-end rate) and one small
+ * kernel expands them to bf_event records on the device right before the batch's launch (the upload itself runs under
+ * the kernel of the previous batch).
+ * Returns the slot, or BF_ERR_ARG when the slice cannot be represented (a coordinate >= 4096, a time step backwards or
+ * a gap of 2^23 ns = 8.4 ms or more between consecutive events): add it with bf_batch_add_packed instead (the whole
+ * batch then travels as 8-byte records).  The results are bit-identical either way. */
+int bf_batch_add_delta(bf_ctx *c, const bf_event *events, int n, int scale, int max_iter, const bf_model *init);
+long long bf_batch_upload_bytes(bf_ctx *c);   /* host-to-device bytes of one bf_batch_run_streamed of the current batch */
+
 /* ---- debug images ----------------------------------------------------------------------------------
  * EventFile::projection_img (event_file.h:460-515): the "motion-compensated event image" the reference dumps with
  * --img / --video (dvs_flow.h:256-260) and publishes from its ROS node.  Per non-noise event: x = int(pr_x * scale),

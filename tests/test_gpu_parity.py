@@ -293,6 +293,61 @@ def test_streamed_upload_of_alternating_batches():
         c.close()
 
 
+def test_delta_upload_format_equals_plain_upload():
+    """bf_batch_add_delta: slices travel as 6-byte delta records and are expanded to bf_event on the device, chunk by
+    chunk, ahead of the minimise kernel -- records must equal those of the plain 8-byte upload bit for bit (the events
+    the kernel sees are identical).  Odd slice lengths (blocks of 1024 end raggedly), noise bits, ping-pong reuse; and
+    the fall-backs: a slice that cannot be represented is refused and the batch then travels in 8-byte format."""
+    import better_flow_b200 as bf
+    st = synth.make_stream(240, 180, 3e6, 0.3, seed=97)
+    sls = synth.cut_slices(st, 0.01)
+    rng = np.random.default_rng(6)
+    packed = []
+    for k, s in enumerate(sls):
+        n = len(s.fr_x) - (k % 7)
+        noise = (rng.uniform(size=n) < 0.01).astype(np.uint8)
+        packed.append(bf.pack_events(s.fr_x[:n], s.fr_y[:n], s.t_ns[:n], noise))
+    n_ev = sum(len(e) for e in packed)
+    c = bf.Context(180, 240, 3, max_events=n_ev + 16, max_slices=len(packed) + 1, device=0)
+    try:
+        for e in packed:
+            c.add_packed(e, 3, 5)
+        assert c.upload_bytes == n_ev * 8 + len(packed) * 120
+        c.run()
+        want = [(r["iters"], r["model"].copy()) for r in c.results()]
+        for rep in range(3):
+            c.reset()
+            for e in packed:
+                c.add_delta(e, 3, 5)
+            assert c.upload_bytes < n_ev * 6.05 + len(packed) * 140
+            c.set_option("upload_chunks", (1, 7, 60)[rep])
+            c.run_streamed()
+            c.sync()
+            for (it, m), r in zip(want, c.results()):
+                assert r["rc"] == 0 and r["iters"] == it and same_model(m, r["model"])
+        # plain run() of a delta batch uses the 8-byte copy the library keeps
+        c.run()
+        assert all(r["iters"] == it for (it, _), r in zip(want, c.results()))
+        # not representable: a gap of more than 8.4 ms, and time running backwards
+        c.reset()
+        bad = packed[0].copy()
+        bad["t_ns"][10:] -= 9_000_000
+        with pytest.raises(bf.BfError):
+            c.add_delta(bad, 3, 5)
+        rev = packed[0][::-1].copy()
+        with pytest.raises(bf.BfError):
+            c.add_delta(rev, 3, 5)
+        assert c.size() == 0
+        c.add_packed(bad, 3, 5)
+        with pytest.raises(bf.BfError):
+            c.add_delta(packed[1], 3, 5)          # the batch already holds an 8-byte slice
+        c.add_packed(packed[1], 3, 5)
+        c.run_streamed(); c.sync()
+        assert c.result(1)["iters"] == want[1][0] and same_model(c.result(1)["model"], want[1][1])
+    finally:
+        c.close()
+
+
 def test_permutation_invariance_bit_exact(ctx240):
     """Integer accumulation makes the result independent of the order of the events -- to the last bit."""
     sl = slices_240(95, 0.03, 1)[0]

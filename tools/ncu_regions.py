@@ -9,7 +9,7 @@ REGION = {  # device function -> region
     "event": ["event_pass", "event_one", "project_event", "event_pixel", "pixel_offset", "mark_cells_bm", "stamp_bit", "flush_stamp_bitmap",
               "slope_time", "warp_from_m", "div_const", "u32_to_double", "make_pixel_map", "ld_nc_u32x4", "ld_state4", "st_state4", "red_add_u64",
               "local_event_pass"],
-    "image": ["image_pass", "cell_process", "compact_cells", "cell_clear", "unpack_avg_fast", "local_cell_process", "acc_zero", "fill_rcp_table"],
+    "image": ["image_pass", "cell_process", "cell_compute", "local_cell_process_s5", "tma_issue_patch", "mbar_wait", "compact_cells", "cell_clear", "unpack_avg_fast", "local_cell_process", "acc_zero", "fill_rcp_table"],
     "reduce+GD": ["acc_block_reduce", "warp_sum", "group_sums", "group_sums_block_gather", "group_sums_block_finish", "opt_advance_warp",
                   "sincos_small", "local_opt_advance", "local_opt_init"],
     "barrier": ["group_barrier", "ld_acquire_u32", "ld_relaxed_u32", "red_release_add_u32", "fence_acq_rel_gpu"],
