@@ -354,7 +354,10 @@ def main():
     ap.add_argument("--cpu-one-core", type=int, default=0, help=argparse.SUPPRESS)   # child mode of one_core_baseline()
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: S slices per GPU (pooled block-cyclic deal at N > 1); strong: ONE stream of S slices sharded over the GPUs")
-    ap.add_argument("--upload-format", default="delta", choices=["delta", "plain"], help="end-to-end path: 6-byte delta records (default) or 8-byte records")
+    ap.add_argument("--upload-format", default="auto", choices=["auto", "delta", "plain"],
+                    help="end-to-end path: 8-byte records or 6-byte delta records (25 %% fewer H2D bytes, expanded by a kernel instance whose "
+                         "loops run ~4 %% slower).  auto = delta from 4 GPUs up, where the ranks share the host's memory / PCIe bandwidth "
+                         "(measured, profiles/r2m_*), plain below")
     ap.add_argument("--opt", default="", help="library options key=value[,key=value] (development: A/B of kernel variants)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -427,7 +430,7 @@ def main():
     ctx.reset()
     upload_format = "6-byte delta records"
     try:
-        if args.upload_format == "plain":
+        if args.upload_format == "plain" or (args.upload_format == "auto" and world < 4):
             raise bf.BfError("plain upload requested")
         for e in mine:
             ctx.add_delta(e, SCALE, MAX_ITER)

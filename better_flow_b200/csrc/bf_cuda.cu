@@ -376,7 +376,7 @@ __device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar
 
 // MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
 // (twice the warps to hide L2 latency, at the price of a few spills).
-template <int MINB>
+template <int MINB, bool DELTA = false>
 __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams P, const __grid_constant__ TmaMaps TM) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -444,6 +444,20 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             const int per = (((n + P.G - 1) / P.G) + 31) & ~31;
             const int lo = rank * per, hi = min(n, lo + per);
             const bf_event *ev = P.events + S.sd.ev_off;
+            if constexpr (DELTA) {
+                // compact upload (bf_batch_add_delta): expand this slice's 6-byte records into the event buffer; the same
+                // pass yields the bounding box.  Only the instance launched by a delta-format streamed run carries this
+                // code -- the register allocation of the kernel is fragile, and the plain instance must not pay for it.
+                delta_expand_slice(P.delta_rec, P.delta_blocks, P.events_w, S.sd.block0, n, rank, P.G, S.scan, S.minmax);
+                const bool any = rank < (n + BF_DELTA_BLOCK - 1) / BF_DELTA_BLOCK;
+                __syncthreads();
+                if (threadIdx.x == 0 && any) {
+                    int *bb = ws->bbox[parity];
+                    atomicMin(&bb[0], S.minmax[0]); atomicMax(&bb[1], S.minmax[1]);
+                    atomicMin(&bb[2], S.minmax[2]); atomicMax(&bb[3], S.minmax[3]);
+                    atomicMin(&bb[4], S.minmax[4]); atomicMax(&bb[5], S.minmax[5]);
+                }
+            } else {
             int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN, tmin = INT_MAX, tmax = INT_MIN;
             for (int i = lo + (int)threadIdx.x; i < hi; i += BF_NT) {
                 const uint2 e = ld_nc_u32x2(ev + i);
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
                 atomicMin(&bb[0], S.minmax[0]); atomicMax(&bb[1], S.minmax[1]);
                 atomicMin(&bb[2], S.minmax[2]); atomicMax(&bb[3], S.minmax[3]);
                 atomicMin(&bb[4], S.minmax[4]); atomicMax(&bb[5], S.minmax[5]);
+            }
             }
         }
         group_barrier(&ws->bar, bar_target, P.G);
@@ -680,53 +695,6 @@ __global__ void bf_stage_project_kernel(int n, const unsigned short *fr_x, const
     }
 }
 
-// ---- compact upload format: 6-byte delta records -> bf_event (include/bf_cuda.h: bf_batch_add_delta) --------------
-struct DeltaBlock {          // up to 1024 consecutive events of one slice
-    long long first;         // index of the block's first event in the batch arrays
-    int count;
-    int t0;                  // local time of the first event
-};
-#define BF_DELTA_BLOCK 1024
-// One CTA of 256 threads per block, 4 consecutive events per thread: t[i] = t0 - (dt[1] + ... + dt[i]).
-__global__ void __launch_bounds__(256) bf_delta_expand_kernel(const unsigned short *rec, const DeltaBlock *blocks, bf_event *out) {
-    __shared__ unsigned warp_tot[8];
-    const DeltaBlock b = blocks[blockIdx.x];
-    const unsigned short *r = rec + (size_t)b.first * 3;
-    const int i0 = (int)threadIdx.x * 4;
-    unsigned x[4], y[4], dt[4];
-    unsigned run = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k;
-        unsigned w0 = 0, w1 = 0, w2 = 0;
-        if (i < b.count) { w0 = r[3 * i]; w1 = r[3 * i + 1]; w2 = r[3 * i + 2]; }
-        x[k] = w0 & 0xfffu;
-        y[k] = (w0 >> 12) | ((w1 & 0xffu) << 4) | ((w1 & 0x100u) ? BF_EVENT_NOISE : 0u);
-        run += (w1 >> 9) | (w2 << 7);
-        dt[k] = run;                                 // inclusive sum within the thread
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    unsigned before = incl - run;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k;
-        if (i < b.count) {
-            bf_event e;
-            e.fr_x = (uint16_t)x[k]; e.fr_y = (uint16_t)y[k]; e.t_ns = b.t0 - (int)(before + dt[k]);
-            out[b.first + i] = e;
-        }
-    }
-}
-
 // ---- EventFile::projection_img (event_file.h:460-515) -------------------------------------------------------------
 // Not a performance path (debug images): four plain per-event / per-pixel kernels.
 __global__ void bf_proj_splat_kernel(int n, const double *pr_x, const double *pr_y, const unsigned char *noise, int scale,
@@ -827,7 +795,7 @@ __global__ void bf_ring_build_kernel(bf_ring_event *ring, long long cap, long lo
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         SliceDesc d;
-        d.ev_off = 0; d.n = n; d.scale = scale; d.max_iter = max_iter; d.has_init = chain ? 2 : 0; d.mode = 0; d.pad_ = 0;
+        d.ev_off = 0; d.n = n; d.scale = scale; d.max_iter = max_iter; d.has_init = chain ? 2 : 0; d.mode = 0; d.block0 = -1;
         d.init.cx = d.init.cy = d.init.dx = d.init.dy = d.init.rot = d.init.div = 0; d.init.cnt = 0; d.init.pad_ = 0;
         d.init.total_dx = d.init.total_dy = d.init.total_rot = d.init.total_div = 0;
         *desc = d;
@@ -1172,6 +1140,7 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
         smem_attr = (int)smem_bytes_min(c);
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
 #if BF_NT <= 256
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
 #endif
@@ -1217,6 +1186,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
         c->smem_pad = (int)std::max(0LL, std::min(value, 64LL * 1024));
         CU(cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
         CU(cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
+        CU(cudaFuncSetAttribute(bf_minimize_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
     }
     else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
     else if (!strcmp(key, "max_grow")) c->max_grow = (int)std::min<long long>(BF_MAX_GROW, std::max(1LL, value));
@@ -1284,6 +1254,7 @@ static int add_desc(bf_ctx *c, long long off, int n, int scale, int max_iter, co
     SliceDesc &d = c->h_slices[c->n_slices];
     memset(&d, 0, sizeof d);
     d.ev_off = off; d.n = n; d.scale = scale; d.max_iter = max_iter;
+    d.block0 = -1;
     d.has_init = init ? 1 : 0;
     if (init) d.init = *init;
     c->uploaded = c->ran = false;
@@ -1356,6 +1327,16 @@ int bf_batch_add_delta(bf_ctx *c, const bf_event *events, int n, int scale, int 
         c->blocks_cap = c->max_events / BF_DELTA_BLOCK + c->max_slices + 2;
         CU(cudaMallocHost(&c->h_delta, (size_t)(c->max_events + 4) * 6));
         CU(cudaMallocHost(&c->h_blocks, (size_t)c->blocks_cap * sizeof(DeltaBlock)));
+        // both device copies (and the second event buffer) now, not inside a later streamed run: cudaMalloc synchronises the device
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMalloc(&c->d_delta[b], (size_t)(c->max_events + 4) * 6));
+            CU(cudaMalloc(&c->d_blocks[b], (size_t)c->blocks_cap * sizeof(DeltaBlock)));
+            if (!c->ev_buf[b]) {
+                CU(cudaMalloc(&c->ev_buf[b], (size_t)(c->max_events + 2) * sizeof(bf_event)));
+                CU(cudaMemset(c->ev_buf[b], 0, (size_t)(c->max_events + 2) * sizeof(bf_event)));
+                CU(cudaMalloc(&c->sl_buf[b], (size_t)c->max_slices * sizeof(SliceDesc)));
+            }
+        }
     }
     const int nb = (n + BF_DELTA_BLOCK - 1) / BF_DELTA_BLOCK;
     if (c->n_blocks + nb > c->blocks_cap) return fail(BF_ERR_ARG, "bf_batch_add_delta: block table full");
@@ -1381,6 +1362,7 @@ int bf_batch_add_delta(bf_ctx *c, const bf_event *events, int n, int scale, int 
     memcpy(c->h_events + c->n_events, events, (size_t)n * sizeof(bf_event));
     const int slot = add_desc(c, c->n_events, n, scale, max_iter, init);
     if (slot < 0) return slot;
+    c->h_slices[slot].block0 = c->n_blocks;
     c->slice_block0.resize((size_t)slot + 2);
     c->slice_block0[(size_t)slot] = c->n_blocks;
     c->n_blocks += nb;
@@ -1422,7 +1404,8 @@ int bf_batch_upload(bf_ctx *c) {
     return BF_OK;
 }
 
-static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready);
+static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready, const unsigned short *delta_rec = nullptr,
+                       const DeltaBlock *delta_blocks = nullptr);
 
 int bf_batch_launch(bf_ctx *c, int want_events) {
     if (!c) return fail(BF_ERR_ARG, "null context");
@@ -1455,30 +1438,6 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     unsigned *d_ready = c->d_ready + 64 * nb, *h_ready = c->h_ready + 64 * nb;
     // the copy engine must not write this buffer before the last launch that read it has finished
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[nb], 0));
-    if (delta) {
-        // Compact upload: the 6-byte records and their block table go up on the copy stream -- under the kernel of the
-        // PREVIOUS batch, which reads the other buffer -- and are expanded to bf_event records by one small kernel on the
-        // compute stream right before this batch's launch.  (The expansion cannot be chunk-streamed under the persistent
-        // kernel like the 8-byte copies below: that kernel holds every register of every SM, so a second kernel would
-        // wait for it while it waits for the events -- measured as a hang, round 2.)
-        CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
-        CU(cudaMemcpyAsync(c->d_delta[nb], c->h_delta, (size_t)c->n_events * 6, cudaMemcpyHostToDevice, c->copy_stream));
-        CU(cudaMemcpyAsync(c->d_blocks[nb], c->h_blocks, (size_t)c->n_blocks * sizeof(DeltaBlock), cudaMemcpyHostToDevice, c->copy_stream));
-        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
-        CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-        if (c->n_blocks > 0) {
-            bf_delta_expand_kernel<<<c->n_blocks, 256, 0, c->stream>>>(c->d_delta[nb], c->d_blocks[nb], c->ev_buf[nb]);
-            CU(cudaGetLastError());
-            c->launches += 1;
-        }
-        c->cur = nb;
-        c->d_events = c->ev_buf[nb];
-        c->d_slices = c->sl_buf[nb];
-        c->uploaded = true;
-        const int rc = launch_impl(c, want_events, nullptr);
-        if (rc != BF_OK) return rc;
-        return bf_batch_download(c);
-    }
     CU(cudaMemsetAsync(d_ready, 0, sizeof(unsigned), c->copy_stream));
     CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copy, c->copy_stream));
@@ -1491,8 +1450,17 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
         if (s1 <= s0) continue;
         const long long lo = c->h_slices[s0].ev_off;
         const long long hi = c->h_slices[s1 - 1].ev_off + c->h_slices[s1 - 1].n;
-        if (hi > lo)
+        if (hi > lo && delta) {
+            // compact upload: the chunk's 6-byte records and block descriptors; the group that takes a slice expands it
+            // into the event buffer in its prologue (delta_expand_slice).  DMA only on this stream: a second kernel could
+            // not run beside the persistent one, which holds every register of every SM.
+            const int b0 = c->slice_block0[(size_t)s0], b1 = c->slice_block0[(size_t)s1];
+            CU(cudaMemcpyAsync(c->d_delta[nb] + lo * 3, c->h_delta + lo * 3, (size_t)(hi - lo) * 6, cudaMemcpyHostToDevice, c->copy_stream));
+            if (b1 > b0)
+                CU(cudaMemcpyAsync(c->d_blocks[nb] + b0, c->h_blocks + b0, (size_t)(b1 - b0) * sizeof(DeltaBlock), cudaMemcpyHostToDevice, c->copy_stream));
+        } else if (hi > lo) {
             CU(cudaMemcpyAsync(c->ev_buf[nb] + lo, c->h_events + lo, (size_t)(hi - lo) * sizeof(bf_event), cudaMemcpyHostToDevice, c->copy_stream));
+        }
         h_ready[k] = (unsigned)s1;
         CU(cudaMemcpyAsync(d_ready, h_ready + k, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
         s0 = s1;
@@ -1501,7 +1469,7 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     c->d_events = c->ev_buf[nb];
     c->d_slices = c->sl_buf[nb];
     c->uploaded = true;
-    int rc = launch_impl(c, want_events, d_ready);
+    int rc = delta ? launch_impl(c, want_events, d_ready, c->d_delta[nb], c->d_blocks[nb]) : launch_impl(c, want_events, d_ready);
     if (rc != BF_OK) return rc;
     return bf_batch_download(c);
 }
@@ -1516,6 +1484,9 @@ struct LaunchSpec {
     const unsigned *ready;
     const bf_slice_result *chain_src; // device record for slices with has_init == 2, or null
     int want_events;
+    bf_event *events_w = nullptr;     // compact upload: writable event buffer + records + block table (else null)
+    const unsigned short *delta_rec = nullptr;
+    const DeltaBlock *delta_blocks = nullptr;
 };
 
 static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
@@ -1540,6 +1511,7 @@ static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
     P.iter_cap = c->iter_cap; P.want_events = L.want_events ? 1 : 0;
     P.ready = L.ready;
     P.chain_src = L.chain_src;
+    P.events_w = L.events_w; P.delta_rec = L.delta_rec; P.delta_blocks = L.delta_blocks;
     P.tma_off = (int)tma_off_of(c); P.tma_tile_elems = tma_tile_elems_of(c);
     P.tab_rows = c->max_scale * c->res_x; P.tab_cols = c->max_scale * c->res_y;
     P.bm_words = bm_words_of(c);
@@ -1566,16 +1538,22 @@ static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
 #if BF_NT <= 256
     if (c->ctas_per_sm == 4) kern = (void *)bf_minimize_kernel<4>;
 #endif
+    if (L.delta_rec != nullptr) {
+        // the instance that expands 6-byte delta records in its prologue (2 CTAs per SM only)
+        if (c->ctas_per_sm != 2) return fail(BF_ERR_STATE, "the compact upload format needs ctas_per_sm = 2");
+        kern = (void *)bf_minimize_kernel<2, true>;
+    }
     CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
     CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this)
     c->launches += 1;
     return BF_OK;
 }
 
-static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready) {
+static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready, const unsigned short *delta_rec, const DeltaBlock *delta_blocks) {
     CU(cudaSetDevice(c->device));
     if (c->n_slices == 0) { c->ran = true; return BF_OK; }
     LaunchSpec L{c->d_events, c->d_slices, c->d_results, c->n_slices, c->n_events, ready, nullptr, want_events};
+    if (delta_rec) { L.events_w = c->d_events; L.delta_rec = delta_rec; L.delta_blocks = delta_blocks; }
     const int rc = launch_spec(c, L);
     if (rc != BF_OK) return rc;
     c->ran = true;

@@ -24,6 +24,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include "bf_logic.h"
@@ -73,9 +74,17 @@ struct SliceDesc {
     int max_iter;
     int has_init;
     int mode;           // 0: OptimizerRolling::run, 1: OptimizerLocal::run
-    int pad_;
+    int block0;         // compact upload (bf_batch_add_delta): first DeltaBlock of the slice, or -1
     bf_model init;
 };
+
+// Compact upload format: up to 1024 consecutive events of one slice as 6-byte delta records (include/bf_cuda.h).
+struct DeltaBlock {
+    long long first;         // index of the block's first event in the batch arrays
+    int count;
+    int t0;                  // local time of the first event
+};
+#define BF_DELTA_BLOCK 1024
 
 // Per-group control block in global memory (one 256-byte record per group).
 struct GroupWs {
@@ -153,6 +162,9 @@ struct KParams {
     unsigned *groups_done;   // groups that found the slice queue empty
     const unsigned *ready;   // optional: number of slices whose events have landed in HBM (streamed upload)
     const bf_slice_result *chain_src;   // optional: record whose model warm-starts a slice with has_init == 2 (bf_ring_slice)
+    bf_event *events_w;      // compact upload: the event buffer, writable (the groups expand their slices into it), else null
+    const unsigned short *delta_rec;   //            the 6-byte records (3 x u16 per event), or null
+    const DeltaBlock *delta_blocks;
     int tma_off;             // BF_TMA_PATCH: byte offset of the per-warp tile buffers in dynamic shared memory (128-byte aligned)
     int tma_tile_elems;      //               u64 elements per warp buffer
     long long *prof;         // optional [gridDim.x][BF_NPROF] cycle counters per phase (debug), else null
@@ -449,6 +461,75 @@ __device__ __forceinline__ void flush_stamp_bitmap(unsigned *bm, unsigned *flags
         } while (m != 0u);
     }
 #endif
+}
+
+// ---- compact upload: a group expands its slice's 6-byte delta records into bf_event records -----------------------
+// CTA `rank` of the G CTAs of the group takes blocks rank, rank + G, ... of the slice (1024 events each, two rounds of
+// BF_NT = 512 events): t[i] = t0 - (dt[1] + ... + dt[i]) by a CTA-wide scan, the 8-byte record is written to the event
+// buffer (read back L2-coherently by every later pass) and folded into the thread's bounding box / time range, so this
+// pass REPLACES the bounding-box pass over the events.  Records and block table were written by the copy engine during
+// this launch (streamed upload): ld.cg only.  Kept out of line: it runs once per slice and must not perturb the register
+// allocation of the per-iteration passes.
+__device__ __forceinline__ unsigned ld_cg_u16(const unsigned short *p) {
+    unsigned short v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (unsigned)v;
+}
+__device__ __noinline__ void delta_expand_slice(const unsigned short *rec, const DeltaBlock *blocks, bf_event *out, int block0, int n,
+                                                int rank, int G, int *scan /* [BF_NW] shared */, int *smm /* 6 ints, shared: min / max pairs */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = (n + BF_DELTA_BLOCK - 1) / BF_DELTA_BLOCK;
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN, tmin = INT_MAX, tmax = INT_MIN;
+    for (int kb = rank; kb < nb; kb += G) {
+        const DeltaBlock *bp = blocks + block0 + kb;
+        const long long first = __ldcg(&bp->first);
+        const int count = __ldcg(&bp->count), t0 = __ldcg(&bp->t0);
+        const unsigned short *r = rec + (size_t)first * 3;
+        unsigned carry = 0;
+        for (int base = 0; base < BF_DELTA_BLOCK; base += BF_NT) {
+            const int i = base + (int)threadIdx.x;
+            unsigned w0 = 0, w1 = 0, w2 = 0;
+            if (i < count) { w0 = ld_cg_u16(r + 3 * i); w1 = ld_cg_u16(r + 3 * i + 1); w2 = ld_cg_u16(r + 3 * i + 2); }
+            const unsigned dt = (w1 >> 9) | (w2 << 7);
+            unsigned incl = dt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            __syncthreads();
+            if (lane == 31) scan[warp] = (int)incl;
+            __syncthreads();
+            unsigned before = carry, total = 0;
+            for (int w = 0; w < BF_NW; ++w) {
+                const unsigned v = (unsigned)scan[w];
+                if (w < warp) before += v;
+                total += v;
+            }
+            if (i < count) {
+                const int fx = (int)(w0 & 0xfffu), fy = (int)((w0 >> 12) | ((w1 & 0xffu) << 4));
+                const int t = t0 - (int)(before + incl);
+                bf_event e;
+                e.fr_x = (uint16_t)fx; e.fr_y = (uint16_t)(fy | ((w1 & 0x100u) ? BF_EVENT_NOISE : 0u)); e.t_ns = t;
+                out[first + i] = e;
+                xmin = min(xmin, fx); xmax = max(xmax, fx); ymin = min(ymin, fy); ymax = max(ymax, fy);
+                tmin = min(tmin, t); tmax = max(tmax, t);
+            }
+            carry += total;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o)); tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    if (lane == 0 && rank < nb) {
+        atomicMin(&smm[0], xmin); atomicMax(&smm[1], xmax);
+        atomicMin(&smm[2], ymin); atomicMax(&smm[3], ymax);
+        atomicMin(&smm[4], tmin); atomicMax(&smm[5], tmax);
+    }
 }
 
 // ---- event pass: clear old pixel, re-project, splat --------------------------------------------

@@ -258,9 +258,9 @@ long long bf_multi_launch_count(bf_multi *m);
  * newest -> oldest, dvs_flow.h:196-198, so local times decrease: dt = t[i-1] - t[i] >= 0), with an absolute local time
  * every 1024 events (one 16-byte block descriptor).  bf_batch_add_delta packs a slice into the context's pinned delta
  * staging; when EVERY slice of a batch was added this way, bf_batch_run_streamed uploads the 6-byte records (25 % fewer
- * bytes: with 8 GPUs on one host the H2D of 8 x 426 MB per step is what bounds the end-to-end rate) and one small
- * kernel expands them to bf_event records on the device right before the batch's launch (the upload itself runs under
- * the kernel of the previous batch).
+ * bytes: with 8 GPUs on one host the H2D of 8 x 426 MB per step is what bounds the end-to-end rate) and the
+ * group of CTAs that takes a slice expands its records into bf_event records in its prologue (the pass that computes
+ * the slice's bounding box anyway), so the upload still streams in chunks under the running kernel.
  * Returns the slot, or BF_ERR_ARG when the slice cannot be represented (a coordinate >= 4096, a time step backwards or
  * a gap of 2^23 ns = 8.4 ms or more between consecutive events): add it with bf_batch_add_packed instead (the whole
  * batch then travels as 8-byte records).  The results are bit-identical either way. */
