@@ -35,6 +35,7 @@ struct __align__(16) Smem {
     int cont;
     int guard;
     int minmax[6];
+    double cpart[BF_NSUMS];                // CLUSTER instances: this CTA's partial sums, read by the peers through DSMEM
 #if BF_TMA_PATCH
     unsigned long long tma_bar[BF_NW];     // one mbarrier per warp (TMA tile staging of the cell patches)
     unsigned tma_phase[BF_NW];
@@ -54,7 +55,7 @@ struct LoopState {
     bool helper;
 };
 
-template <int SH>
+template <int SH, bool CLUSTER = false>
 __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMaps *tm) {
     GroupWs *ws = P.ws + L.vgroup;
     u64 *img0 = P.images + (size_t)L.vgroup * 2 * P.img_elems;
@@ -65,7 +66,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMap
     const int i0 = S.g.rows / 2, j0 = S.g.cols / 2;
     const int rank = L.rank;
     const bool leader = !L.helper && rank == 0 && threadIdx.x == 0;
-    const bool may_grow = P.allow_help != 0;   // (earlier helpers are full members: they must follow later growth too)
+    const bool may_grow = !CLUSTER && P.allow_help != 0;   // (earlier helpers are full members: they must follow later growth too)
 
     // per-slice cell tables live behind the fixed part of the shared-memory block
     int2 *row_tab = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(&S) + sizeof(Smem));
@@ -98,7 +99,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMap
         if (pf) __syncthreads();
         PF_MARK(PF_EVENT);
         {
-            const long long sp = group_barrier(&ws->bar, bar_target, G);   // A: all splats of this iteration are in L2
+            const long long sp = sync_group<CLUSTER>(&ws->bar, bar_target, G);   // A: all splats of this iteration are in L2
             if (prof) pf[PF_BAR_A_SPIN] += sp;
         }
         PF_MARK(PF_BAR_A);
@@ -127,7 +128,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMap
 #endif
         if (pf) __syncthreads();
         PF_MARK(PF_CELLS);
-        acc_block_reduce(acc, S.red, partials + rank * BF_NSUMS);
+        acc_block_reduce(acc, S.red, CLUSTER ? S.cpart : partials + rank * BF_NSUMS);
         PF_MARK(PF_REDUCE);
         // HELPING, victim side: the leader's decision to let a claimed helper in travels with barrier B
         // (and once the previous helper is in, the slice is opened again for the next one, up to BF_MAX_GROW groups)
@@ -137,17 +138,18 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMap
             else if (st == (unsigned)HELP_JOINED && G + P.G <= P.max_grow * P.G) atomicExch(&ws->help_state, (unsigned)HELP_OPEN);
         }
         {
-            const long long sp = group_barrier(&ws->bar, bar_target, G);   // B: all partial sums are visible
+            const long long sp = sync_group<CLUSTER>(&ws->bar, bar_target, G);   // B: all partial sums are visible
             if (prof) pf[PF_BAR_B_SPIN] += sp;
         }
         PF_MARK(PF_BAR_B);
         const bool grow = may_grow && __ldcg(&ws->grow_iter) == iter;
 
-        const bool block_gather = G >= BF_BLOCK_GATHER_MIN && G <= BF_NT;
+        const bool block_gather = !CLUSTER && G >= BF_BLOCK_GATHER_MIN && G <= BF_NT;
         if (block_gather) group_sums_block_gather(partials, G, S.red);
         if (threadIdx.x < 32) {
             BfSums s;
-            if (block_gather) group_sums_block_finish(s, S.red);
+            if constexpr (CLUSTER) group_sums_dsmem(s, S.cpart, G);
+            else if (block_gather) group_sums_block_finish(s, S.red);
             else group_sums(s, partials, G, pf ? pf + 14 : nullptr);
             PF_MARK(PF_SCAN);   // (slot reused: time of the partial-sum gather)
             const bool cont = opt_advance_warp(S.opt, S.g, s, i0, j0, S.sd.max_iter, P.iter_cap, S.proj);
@@ -196,7 +198,7 @@ __device__ void slice_loop(const KParams &P, Smem &S, LoopState &L, const TmaMap
 }
 
 // OptimizerRolling::run for the slice in S.sd, owned by this CTA's group.
-template <int SH>
+template <int SH, bool CLUSTER = false>
 __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_target, unsigned &tag, int group,
                           int rank, const TmaMaps *tm) {
     if (threadIdx.x == 0) {
@@ -215,7 +217,7 @@ __device__ void run_slice(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar_
     LoopState L;
     L.vgroup = group; L.rank = rank; L.G = P.G; L.iter = 0; L.buf = 0; L.n_prev = -1;
     L.tag = tag; L.bar_target = bar_target; L.helper = false;
-    slice_loop<SH>(P, S, L, tm);
+    slice_loop<SH, CLUSTER>(P, S, L, tm);
     tag = L.tag; bar_target = L.bar_target;
     // the slice is over: nobody can join any more (a helper that had claimed but not joined sees 0 and leaves)
     if (P.allow_help && rank == 0 && threadIdx.x == 0) atomicExch(&ws->help_state, (unsigned)HELP_CLOSED);
@@ -376,7 +378,10 @@ __device__ void help_phase(const KParams &P, Smem &S, GroupWs *ws, unsigned &bar
 
 // MINB = resident CTAs per SM the instance is compiled for: 1 -> 128 registers/thread, 2 -> 64
 // (twice the warps to hide L2 latency, at the price of a few spills).
-template <int MINB, bool DELTA = false>
+// MINB = resident CTAs per SM the instance is compiled for; DELTA = expands the compact upload format in its prologue;
+// CLUSTER = every group is one thread-block cluster (hardware barrier, partial sums through distributed shared memory;
+// rolling slices only, no tail helping): the single-slice / warm-start-chain instance.
+template <int MINB, bool DELTA = false, bool CLUSTER = false>
 __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams P, const __grid_constant__ TmaMaps TM) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -417,11 +422,13 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             bb[0] = INT_MAX; bb[1] = INT_MIN; bb[2] = INT_MAX; bb[3] = INT_MIN; bb[4] = INT_MAX; bb[5] = INT_MIN;
             ws->cur_slice = s;
         }
-        group_barrier(&ws->bar, bar_target, P.G);
+        sync_group<CLUSTER>(&ws->bar, bar_target, P.G);
         const int slice = __ldcg(&ws->cur_slice);
         if (slice >= P.n_slices) {
-            if (!P.allow_help) break;
-            help_phase(P, S, ws, bar_target, group, rank, &TM);   // HELPING, helper side: returns when nothing is left to help
+            if constexpr (!CLUSTER) {
+                if (!P.allow_help) break;
+                help_phase(P, S, ws, bar_target, group, rank, &TM);   // HELPING, helper side: returns when nothing is left to help
+            }
             break;
         }
         if (threadIdx.x == 0) {
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
             }
             }
         }
-        group_barrier(&ws->bar, bar_target, P.G);
+        sync_group<CLUSTER>(&ws->bar, bar_target, P.G);
 
         // ---- geometry + guards (optimizer_rolling.h:248-283, 49-58) ---------------------------
         if (threadIdx.x == 0) {
@@ -510,15 +517,17 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
         const int guard = S.guard;
         if (pf && threadIdx.x == 0) pf[PF_PROLOGUE] += clock64() - t_pro;
 
-        if (guard == 0 && S.sd.mode == 1) {
-            if (S.sd.scale == 1) run_slice_local<0>(P, S, ws, bar_target, tag, group, rank);
-            else if (S.sd.scale == 3) run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
-            else run_slice_local<2>(P, S, ws, bar_target, tag, group, rank);
+        if (!CLUSTER && guard == 0 && S.sd.mode == 1) {
+            if constexpr (!CLUSTER) {
+                if (S.sd.scale == 1) run_slice_local<0>(P, S, ws, bar_target, tag, group, rank);
+                else if (S.sd.scale == 3) run_slice_local<1>(P, S, ws, bar_target, tag, group, rank);
+                else run_slice_local<2>(P, S, ws, bar_target, tag, group, rank);
+            }
         } else if (guard == 0) {
             switch (S.sd.scale) {
-                case 1: run_slice<0>(P, S, ws, bar_target, tag, group, rank, &TM); break;
-                case 3: run_slice<1>(P, S, ws, bar_target, tag, group, rank, &TM); break;
-                default: run_slice<2>(P, S, ws, bar_target, tag, group, rank, &TM); break;
+                case 1: run_slice<0, CLUSTER>(P, S, ws, bar_target, tag, group, rank, &TM); break;
+                case 3: run_slice<1, CLUSTER>(P, S, ws, bar_target, tag, group, rank, &TM); break;
+                default: run_slice<2, CLUSTER>(P, S, ws, bar_target, tag, group, rank, &TM); break;
             }
         } else if (threadIdx.x == 0) {
             bf_opt_init(S.opt, S.sd.has_init ? &S.sd.init : nullptr);
@@ -558,6 +567,7 @@ __global__ void __launch_bounds__(BF_NT, MINB) bf_minimize_kernel(const KParams 
         parity ^= 1;
     }
     if (pf && threadIdx.x == 0) pf[PF_TOTAL] += clock64() - t_begin;
+    if constexpr (CLUSTER) cluster_barrier();   // no CTA may exit while a peer can still read its shared memory
 }
 
 // ---- stage-level kernels (AccelLib surface; same device functions as the persistent kernel) ----
@@ -862,6 +872,9 @@ struct bf_ctx {
     int n_groups_alloc = 0;
     int iter_cap = 20000;
     int min_events = 1000;
+    int cluster = 0;            // batch launches: 0 = groups on the global-memory barrier; 2..16 = every group is one thread-block cluster of that many CTAs
+    int ring_cluster = 0;       // the same for the single-slice launches of bf_ring_slice (the warm-start chain)
+    int cluster_max[BF_MAX_CLUSTER + 1] = {0};   // cudaOccupancyMaxActiveClusters per cluster size (0 = not queried yet)
     int smem_pad = 0;           // experiment knob: extra dynamic shared memory per CTA (shrinks the L1 carve-out)
     int tail_help = 1;          // idle groups join slices that are still running when the queue is empty
     int max_grow = 8;           // ... up to this many groups per slice
@@ -1141,6 +1154,8 @@ bf_ctx *bf_ctx_create(int sensor_rows, int sensor_cols, int max_scale, long long
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+        if ((e = cudaFuncSetAttribute(bf_minimize_kernel<2, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
 #if BF_NT <= 256
         if ((e = cudaFuncSetAttribute(bf_minimize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr)) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
 #endif
@@ -1182,11 +1197,16 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     else if (!strcmp(key, "min_group")) c->min_group = (int)std::max(1LL, value);
     else if (!strcmp(key, "image_budget_mb")) c->image_budget_mb = std::max(1LL, value);
     else if (!strcmp(key, "profile")) c->profile = (int)value;
+    else if (!strcmp(key, "cluster") || !strcmp(key, "ring_cluster")) {
+        if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16) return fail(BF_ERR_ARG, "%s must be 0, 2, 4, 8 or 16", key);
+        (key[0] == 'c' ? c->cluster : c->ring_cluster) = (int)value;
+    }
     else if (!strcmp(key, "smem_pad")) {
         c->smem_pad = (int)std::max(0LL, std::min(value, 64LL * 1024));
         CU(cudaFuncSetAttribute(bf_minimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
         CU(cudaFuncSetAttribute(bf_minimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
         CU(cudaFuncSetAttribute(bf_minimize_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
+        CU(cudaFuncSetAttribute(bf_minimize_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_min(c)));
     }
     else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
     else if (!strcmp(key, "max_grow")) c->max_grow = (int)std::min<long long>(BF_MAX_GROW, std::max(1LL, value));
@@ -1209,6 +1229,8 @@ long long bf_ctx_get_option(bf_ctx *c, const char *key) {
     if (!strcmp(key, "ctas_per_sm")) return c->ctas_per_sm;
     if (!strcmp(key, "image_bytes")) return c->img_elems * 8;
     if (!strcmp(key, "smem_bytes")) return (long long)smem_bytes_min(c);
+    if (!strcmp(key, "cluster")) return c->cluster;
+    if (!strcmp(key, "ring_cluster")) return c->ring_cluster;
     return -1;
 }
 
@@ -1484,6 +1506,7 @@ struct LaunchSpec {
     const unsigned *ready;
     const bf_slice_result *chain_src; // device record for slices with has_init == 2, or null
     int want_events;
+    int cluster = 0;                  // > 0: launch the CLUSTER instance with groups = thread-block clusters of this many CTAs
     bf_event *events_w = nullptr;     // compact upload: writable event buffer + records + block table (else null)
     const unsigned short *delta_rec = nullptr;
     const DeltaBlock *delta_blocks = nullptr;
@@ -1543,6 +1566,29 @@ static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
         if (c->ctas_per_sm != 2) return fail(BF_ERR_STATE, "the compact upload format needs ctas_per_sm = 2");
         kern = (void *)bf_minimize_kernel<2, true>;
     }
+    if (L.cluster > 0 && L.delta_rec == nullptr && c->ctas_per_sm == 2) {
+        // CLUSTER instance: one thread-block cluster per group.  No cooperative launch is needed: clusters never wait for
+        // each other (no tail helping), and the CTAs of one cluster are co-scheduled by the hardware.
+        const int cs = L.cluster;
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(BF_NT); cfg.dynamicSmemBytes = smem_bytes_min(c); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (c->cluster_max[cs] == 0) {
+            cfg.gridDim = dim3((unsigned)cs);
+            int n = 0;
+            CU(cudaOccupancyMaxActiveClusters(&n, bf_minimize_kernel<2, false, true>, &cfg));
+            if (n < 1) return fail(BF_ERR_CUDA, "clusters of %d CTAs cannot be scheduled on this device", cs);
+            c->cluster_max[cs] = n;
+        }
+        c->G = cs;
+        c->n_groups = std::max(1, std::min(std::min(L.n_slices, c->n_groups_alloc), c->cluster_max[cs]));
+        P.G = cs; P.allow_help = 0; P.max_grow = 1; P.part_stride = cs;
+        cfg.gridDim = dim3((unsigned)(c->n_groups * cs));
+        CU(cudaLaunchKernelEx(&cfg, bf_minimize_kernel<2, false, true>, P, c->tmaps));
+    } else
     CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
     CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this)
     c->launches += 1;
@@ -1553,6 +1599,9 @@ static int launch_impl(bf_ctx *c, int want_events, const unsigned *ready, const 
     CU(cudaSetDevice(c->device));
     if (c->n_slices == 0) { c->ran = true; return BF_OK; }
     LaunchSpec L{c->d_events, c->d_slices, c->d_results, c->n_slices, c->n_events, ready, nullptr, want_events};
+    L.cluster = c->cluster;
+    for (int k = 0; k < c->n_slices && L.cluster > 0; ++k)
+        if (c->h_slices[k].mode != 0) L.cluster = 0;          // (the CLUSTER instance runs OptimizerRolling slices only)
     if (delta_rec) { L.events_w = c->d_events; L.delta_rec = delta_rec; L.delta_blocks = delta_blocks; }
     const int rc = launch_spec(c, L);
     if (rc != BF_OK) return rc;
@@ -1948,6 +1997,7 @@ int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_it
     CU(cudaGetLastError());
     c->launches += 1;
     LaunchSpec L{c->d_events, r->d_desc + slot, r->d_res + slot, 1, (long long)n, nullptr, prev, 0};
+    L.cluster = c->ring_cluster;
     const int rc = launch_spec(c, L);
     if (rc != BF_OK) return rc;
     CU(cudaMemcpyAsync(r->h_res + slot, r->d_res + slot, sizeof(bf_slice_result), cudaMemcpyDeviceToHost, c->stream));

@@ -290,6 +290,36 @@ __device__ __forceinline__ long long group_barrier(unsigned *counter, unsigned &
     return spin;   // cycles thread 0 spent between its arrival and the release (valid in thread 0)
 }
 
+// ---- thread-block-cluster flavour of the group (CLUSTER instances of the kernel) ----------------------------------
+// When a group of G <= 16 CTAs is launched as ONE thread-block cluster, its barrier is the hardware cluster barrier
+// (barrier.cluster.arrive.release / wait.acquire -> UCGABAR_ARV / UCGABAR_WAIT; every thread arrives, so every thread's
+// splats are released: no bar.sync + thread-0 handshake through a global counter) and the per-CTA partial sums are read
+// straight out of the peers' shared memory (mapa + ld.shared::cluster: distributed shared memory) instead of going
+// through global memory.  Used for the latency-bound case -- ONE slice at a time, the warm-start chain of DVS_flow's
+// default mode -- where the ~2 x 3 us of the global-memory barrier and the partial-sum round trip are a third of an
+// iteration; for throughput batches the 2-CTA... 4-CTA groups on the global barrier stay (clusters of 8 strand SMs on
+// this GPU and larger groups lose).
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double *own_smem, unsigned peer_rank) {
+    unsigned ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned)__cvta_generic_to_shared(own_smem)), "r"(peer_rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+template <bool CLUSTER>
+__device__ __forceinline__ long long sync_group(unsigned *counter, unsigned &target, int G) {
+    if constexpr (CLUSTER) {
+        cluster_barrier();
+        return 0;
+    } else {
+        return group_barrier(counter, target, G);
+    }
+}
+#define BF_MAX_CLUSTER 16
+
 // ---- exact division by the two constants of Event::apply_project (event.h:164-168) ----------
 // q = fma(fma(-b, a*r, a), r, a*r) with r = rn(1/b) equals the correctly rounded a / b for EVERY
 // finite f32-valued a, for b = 127 and b = 10000 (checked exhaustively over all 2^32 floats,
@@ -1261,6 +1291,19 @@ __device__ __forceinline__ void group_sums(BfSums &s, const double *partials, in
     }
     // The lane-strided loop diverges.  Without an explicit reconvergence point the shuffles below run
     // through the compiler's divergent-warp fallback (BRA.DIV handlers): measured 23.8k vs 1.9k cycles.
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) v[k] = warp_sum(v[k]);
+    s.cnt = v[0]; s.si = v[1]; s.sj = v[2]; s.sgx = v[3]; s.sgy = v[4];
+    s.sigx = v[5]; s.sjgx = v[6]; s.sigy = v[7]; s.sjgy = v[8];
+}
+
+// CLUSTER flavour: record r is read from CTA r's shared memory (distributed shared memory).  Warp 0, all lanes.
+__device__ __forceinline__ void group_sums_dsmem(BfSums &s, const double *own_record /* shared, BF_NSUMS doubles */, int G) {
+    const int lane = threadIdx.x & 31;
+    double v[BF_NSUMS];
+#pragma unroll
+    for (int k = 0; k < BF_NSUMS; ++k) v[k] = lane < G ? ld_dsmem_f64(own_record + k, (unsigned)lane) : 0.0;
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < BF_NSUMS; ++k) v[k] = warp_sum(v[k]);

@@ -53,6 +53,9 @@ public:
                 std::cerr << "bf_ctx_create failed: " << bf_last_error() << std::endl;
                 std::exit(1);
             }
+            // development knobs for same-box A/B runs of the tool (tools/cli_ring.py)
+            if (const char *v = std::getenv("BF_RING_CLUSTER")) bf_ctx_set_option(s.ctx, "ring_cluster", atoi(v));
+            if (const char *v = std::getenv("BF_CLUSTER")) bf_ctx_set_option(s.ctx, "cluster", atoi(v));
             if (std::getenv("BF_TIMING"))
                 std::cerr << "[timing] context (re)created for " << s.events << " events / " << s.slices << " slices in "
                           << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;

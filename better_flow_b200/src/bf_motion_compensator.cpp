@@ -219,7 +219,9 @@ int main(int argc, char *argv[]) {
         }
         clock_t end = std::clock();
         std::cout << "Toatal flow elapsed: " << double(end - begin) / CLOCKS_PER_SEC << " sec." << std::endl << std::flush;
+        const double host_loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - proc0).count();
         if (timing) {
+            std::cerr << "[timing] add_event loop returned after " << host_loop_s << " s (with the device ring: slices are only enqueued)" << std::endl;
             // wall time of the processing proper (events already in memory): add_event loop + the final slice + every
             // model read back.  (The reference's figure above is std::clock(): CPU time, summed over threads.)
             estimator.recompute();

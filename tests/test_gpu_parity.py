@@ -348,6 +348,46 @@ def test_delta_upload_format_equals_plain_upload():
         c.close()
 
 
+@pytest.mark.parametrize("cs", [2, 4, 8, 16])
+def test_cluster_instance_equals_the_default_path(cs):
+    """The CLUSTER instance of the kernel (every group = one thread-block cluster: hardware cluster barrier, partial sums
+    read from the peers' shared memory) against the default instance on the global-memory barrier: same iteration counts
+    and dividers, flow equal up to the order of the fp64 partial sums.  Scales 1 / 3 / 5, warm starts, a skipped slice,
+    per-event read-back, more slices than clusters fit, repeated launches."""
+    import better_flow_b200 as bf
+    st = synth.make_stream(240, 180, 3e6, 0.012 * 40, seed=123)
+    sls = synth.cut_slices(st, 0.012)[:40]
+    init = np.array([90.0, 120.0, 0, 0, 0, 0, 0, 0.01, -0.02, 1e-5, -2e-5])
+    c = bf.Context(180, 240, 5, max_events=len(st) + 4096, max_slices=64, device=0)
+    try:
+        def fill():
+            c.reset()
+            for k, s in enumerate(sls):
+                c.add(s.fr_x, s.fr_y, s.t_ns, (1, 3, 5)[k % 3], (-1, 6, 12)[k % 3], init=init if k % 5 == 4 else None)
+            c.add(sls[0].fr_x[:500], sls[0].fr_y[:500], sls[0].t_ns[:500], 3, -1)      # below the 1000-event guard
+        fill()
+        c.run(want_events=True)
+        want = c.results()
+        want_ev = c.events(7, len(sls[7].fr_x))
+        c.set_option("cluster", cs)
+        for rep in range(2):
+            fill()
+            c.run(want_events=True)
+            assert c.get_option("group_size") == cs
+            for w, g in zip(want, c.results()):
+                assert g["rc"] == w["rc"] and g["iters"] == w["iters"] and g["dividers"].tobytes() == w["dividers"].tobytes()
+                assert same_model(g["model"], w["model"], rtol=1e-11)
+            ev = c.events(7, len(sls[7].fr_x))
+            assert np.allclose(ev["pr_x"], want_ev["pr_x"], rtol=0, atol=1e-9) and np.allclose(ev["nx"], want_ev["nx"], rtol=0, atol=1e-12)
+        # a single slice on one cluster (what bf_ring_slice launches)
+        one = c.minimize(sls[3].fr_x, sls[3].fr_y, sls[3].t_ns, 3, -1)
+        c.set_option("cluster", 0)
+        ref1 = c.minimize(sls[3].fr_x, sls[3].fr_y, sls[3].t_ns, 3, -1)
+        assert one["iters"] == ref1["iters"] and same_model(one["model"], ref1["model"], rtol=1e-11)
+    finally:
+        c.close()
+
+
 def test_permutation_invariance_bit_exact(ctx240):
     """Integer accumulation makes the result independent of the order of the events -- to the last bit."""
     sl = slices_240(95, 0.03, 1)[0]

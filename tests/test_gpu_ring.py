@@ -38,13 +38,19 @@ def _ring_chain(ctx, fr_x, fr_y, ts, consumed, max_iter, chain, capacity=50000, 
         ring.close()
 
 
+@pytest.mark.parametrize("ring_cluster", [0, 8, 16])
 @pytest.mark.parametrize("chain", [True, False])
-def test_ring_chain_equals_host_driven_chain(ctx240, chain):
+def test_ring_chain_equals_host_driven_chain(ctx240, chain, ring_cluster):
     st = synth.make_stream(240, 180, 1.5e6, 0.2, seed=77, vel=(60.0, 35.0), omega=0.4)
     fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.int64)
     consumed = list(range(20000, len(ts), 20000))
+    ctx240.set_option("ring_cluster", 0)
     want = _host_chain(ctx240, fr_x, fr_y, ts, consumed, -1, chain)
-    got, first = _ring_chain(ctx240, fr_x, fr_y, ts, consumed, -1, chain, max_pending=len(consumed))
+    ctx240.set_option("ring_cluster", ring_cluster)       # the single-slice launches of the ring on one thread-block cluster
+    try:
+        got, first = _ring_chain(ctx240, fr_x, fr_y, ts, consumed, -1, chain, max_pending=len(consumed))
+    finally:
+        ctx240.set_option("ring_cluster", 0)
     assert first == 0 and len(got) == len(want) >= 10
     for w, g in zip(want, got):
         assert g["rc"] == w["rc"] == 0 and g["iters"] == w["iters"] and g["n_events"] == w["n_events"]

@@ -20,20 +20,24 @@ rec.tofile(binf)
 print("stream: %d events, %.2f s of sensor time" % (len(st), dur))
 out = {"events": len(st)}
 PROC = re.compile(r"\[timing\] processing (\d+) events in ([0-9.e+-]+) s = ([0-9.e+-]+) Mev/s, slices (\d+)")
-def run(extra, label, key):
+def run(extra, label, key, env=None):
     best = None
     for rep in range(3):
         flow = "/tmp/flow_%s.txt" % key
-        r = subprocess.run([CLI, "--quiet", "--flow-out=" + flow] + extra + [binf], capture_output=True, text=True, env=dict(os.environ, BF_TIMING="1"))
+        r = subprocess.run([CLI, "--quiet", "--flow-out=" + flow] + extra + [binf], capture_output=True, text=True, env=dict(os.environ, BF_TIMING="1", **(env or {})))
         m = PROC.search(r.stderr)
         if r.returncode != 0 or not m:
             print(label, "FAILED", r.stderr[-400:]); return None
-        v = (float(m.group(2)), float(m.group(3)), int(m.group(4)))
+        h = re.search(r"add_event loop returned after ([0-9.e+-]+) s", r.stderr)
+        v = (float(m.group(2)), float(m.group(3)), int(m.group(4)), float(h.group(1)) if h else -1.0)
         best = v if best is None or v[0] < best[0] else best
-    print("%-52s processing %.4f s  %8.1f Mev/s  %d slices" % (label, best[0], best[1], best[2]))
-    out[key] = {"seconds": best[0], "mevs": best[1], "slices": best[2]}
+    print("%-52s processing %.4f s  %8.1f Mev/s  %d slices  (add_event loop returned after %.4f s)" % (label, best[0], best[1], best[2], best[3]))
+    out[key] = {"seconds": best[0], "mevs": best[1], "slices": best[2], "host_loop_seconds": best[3]}
     return np.loadtxt(flow, ndmin=2)
 a = run([], "default mode, device ring", "default_ring")
+for cs in (8, 16):
+    run([], "default mode, device ring, cluster of %d" % cs, "default_ring_cluster%d" % cs, env={"BF_RING_CLUSTER": str(cs)})
+    run(["--stm-disable"], "--stm-disable, device ring, cluster of %d" % cs, "stm_ring_cluster%d" % cs, env={"BF_RING_CLUSTER": str(cs)})
 b = run(["--no-device-ring"], "default mode, host ring (round 1 path)", "default_host")
 c = run(["--stm-disable"], "--stm-disable, device ring", "stm_ring")
 d = run(["--stm-disable", "--no-device-ring"], "--stm-disable, host ring", "stm_host")
