@@ -215,7 +215,7 @@ def class_surface_e2e(device_index):
                 best = None
                 for _ in range(2):
                     r = subprocess.run([cli, "--quiet", "--device=%d" % device_index] + extra + [binf], capture_output=True, text=True,
-                                       env=dict(os.environ, BF_TIMING="1"), timeout=120)
+                                       env=dict(os.environ, BF_TIMING="1"), timeout=45)   # (a TimeoutExpired abandons the whole extra)
                     m = re.search(r"\[timing\] processing (\d+) events in ([0-9.e+-]+) s = ([0-9.e+-]+) Mev/s, slices (\d+)", r.stderr)
                     if r.returncode == 0 and m and (best is None or float(m.group(2)) < best[0]):
                         best = (float(m.group(2)), float(m.group(3)), int(m.group(4)))
@@ -354,10 +354,10 @@ def main():
     ap.add_argument("--cpu-one-core", type=int, default=0, help=argparse.SUPPRESS)   # child mode of one_core_baseline()
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: S slices per GPU (pooled block-cyclic deal at N > 1); strong: ONE stream of S slices sharded over the GPUs")
-    ap.add_argument("--upload-format", default="auto", choices=["auto", "delta", "plain"],
-                    help="end-to-end path: 8-byte records or 6-byte delta records (25 %% fewer H2D bytes, expanded by a kernel instance whose "
-                         "loops run ~4 %% slower).  auto = delta from 4 GPUs up, where the ranks share the host's memory / PCIe bandwidth "
-                         "(measured, profiles/r2m_*), plain below")
+    ap.add_argument("--upload-format", default="plain", choices=["plain", "delta"],
+                    help="end-to-end path: 8-byte records (default) or 6-byte delta records (25 %% fewer H2D bytes; at 8 GPUs, where four of them "
+                         "share one host link, 28.6 instead of 22.7 Gev/s end to end: profiles/r2m_*).  Opt-in: with the 1280x720 configuration on 4 "
+                         "GPUs two of three runs stalled in the delta instance of the kernel (not reproduced on one GPU, unexplained: DESIGN.md 12)")
     ap.add_argument("--opt", default="", help="library options key=value[,key=value] (development: A/B of kernel variants)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -389,7 +389,9 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # (a short collective timeout: should a rank ever stall, the run must fail within minutes, not after NCCL's default 10)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     import better_flow_b200.shard as shard
 
@@ -430,7 +432,7 @@ def main():
     ctx.reset()
     upload_format = "6-byte delta records"
     try:
-        if args.upload_format == "plain" or (args.upload_format == "auto" and world < 4):
+        if args.upload_format == "plain":
             raise bf.BfError("plain upload requested")
         for e in mine:
             ctx.add_delta(e, SCALE, MAX_ITER)

@@ -1460,7 +1460,11 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     unsigned *d_ready = c->d_ready + 64 * nb, *h_ready = c->h_ready + 64 * nb;
     // the copy engine must not write this buffer before the last launch that read it has finished
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[nb], 0));
-    CU(cudaMemsetAsync(d_ready, 0, sizeof(unsigned), c->copy_stream));
+    // (reset by a COPY of a pinned zero, not by cudaMemsetAsync: a small memset may be executed by a kernel, and a kernel on
+    // this stream cannot run while the persistent kernel holds every SM -- the copies queued behind it would then never
+    // start and the persistent kernel would wait for them for ever; only DMA operations may go on the copy stream)
+    h_ready[63] = 0u;
+    CU(cudaMemcpyAsync(d_ready, h_ready + 63, sizeof(unsigned), cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(c->sl_buf[nb], c->h_slices, (size_t)c->n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copy, c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));

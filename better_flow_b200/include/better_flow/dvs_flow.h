@@ -29,6 +29,7 @@
 #define BF_DVS_FLOW_H
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <fstream>
 #include <map>
@@ -102,6 +103,11 @@ protected:
     std::vector<bf_ring_event> ring_new_;    // events pushed since the last slice
     struct Deferred { SliceLog log; int ticket; };
     std::deque<Deferred> deferred_;          // slices enqueued on the device whose models have not been read back yet
+    double t_push_ = 0, t_slice_ = 0, t_resolve_ = 0;   // host seconds spent in bf_ring_push / bf_ring_slice / bf_ring_result
+public:
+    // (BF_TIMING diagnostics of the tool) host time spent inside the ring's three entry points
+    void ring_host_seconds(double &push, double &slice, double &resolve) const { push = t_push_; slice = t_slice_; resolve = t_resolve_; }
+protected:
 
 public:
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time = 0)
@@ -546,8 +552,11 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
         }
         for (auto &d : deferred_) (void)d;   // (tickets of a destroyed ring cannot be outstanding: resolve_deferred runs before a re-creation can be seen)
     }
+    const auto tp0 = std::chrono::steady_clock::now();
     check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
     ring_new_.clear();
+    const auto tp1 = std::chrono::steady_clock::now();
+    t_push_ += std::chrono::duration<double>(tp1 - tp0).count();
     if (log.size > 0) {
         const sll t_new = (sll)(log.ts_first - start), t_old = (sll)(log.ts_last - start);
         if (t_new > INT32_MAX || t_old > INT32_MAX || t_new < INT32_MIN || t_old < INT32_MIN) {
@@ -555,8 +564,10 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
             std::exit(1);
         }
     }
+    const auto ts0 = std::chrono::steady_clock::now();
     const int ticket = bf_ring_slice(ring_, (int)log.size, start, scale, max_iter, stm_disable ? 0 : 1);
     check(ticket, "bf_ring_slice");
+    t_slice_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
     deferred_.push_back(Deferred{log, ticket});
     // the reference dumps every remembered slice after each recompute: that needs the model now
     if (!quiet_ || (int)deferred_.size() >= ring_pending_ - 1) resolve_deferred();
@@ -567,7 +578,10 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::resolve_deferred
         Deferred d = deferred_.front();
         deferred_.pop_front();
         bf_slice_result res;
-        if (bf_ring_result(ring_, d.ticket, &res) < 0) {
+        const auto tr0 = std::chrono::steady_clock::now();
+        const int rrc = bf_ring_result(ring_, d.ticket, &res);
+        t_resolve_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count();
+        if (rrc < 0) {
             std::cerr << "bf_ring_result failed: " << bf_last_error() << std::endl;
             std::exit(1);
         }

@@ -228,6 +228,11 @@ int main(int argc, char *argv[]) {
             estimator.flush();
             final_done = true;
             const double w = std::chrono::duration<double>(std::chrono::steady_clock::now() - proc0).count();
+            double tp = 0, ts = 0, tr = 0;
+            estimator.ring_host_seconds(tp, ts, tr);
+            if (tp + ts + tr > 0)
+                std::cerr << "[timing] device ring, host seconds inside bf_ring_push " << tp << ", bf_ring_slice " << ts
+                          << ", bf_ring_result (waiting for the GPU) " << tr << std::endl;
             std::cerr << "[timing] processing " << i << " events in " << w << " s = " << double(i) / w / 1e6 << " Mev/s, slices "
                       << estimator.slices_done() << std::endl;
         }
