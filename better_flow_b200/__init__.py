@@ -65,7 +65,7 @@ ABI_SYMBOLS = (
     "bf_multi_create", "bf_multi_destroy", "bf_multi_device_count", "bf_multi_set_option", "bf_multi_owner",
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
-    "bf_projection_img", "bf_batch_add_delta", "bf_batch_upload_bytes",
+    "bf_projection_img", "bf_color_time_img", "bf_batch_add_delta", "bf_batch_upload_bytes",
     "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed",
 )
 
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
         lib.bf_batch_add_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.bf_batch_upload_bytes.argtypes = [C.c_void_p]
         lib.bf_batch_upload_bytes.restype = C.c_longlong
+        lib.bf_color_time_img.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.bf_projection_img.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.bf_ring_create.restype = C.c_void_p
         lib.bf_ring_create.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
@@ -394,6 +395,16 @@ class Context:
         avg = np.zeros(1)
         self._chk(self.lib.bf_projection_img(self.h, len(px), _ptr(px), _ptr(py), _ptr(nz), scale, _ptr(out), _ptr(avg)))
         return out, float(avg[0])
+
+    def color_time_img(self, pr_x, pr_y, t_ns, scale=3, noise=None):
+        """EventFile::color_time_img: uint8 BGR image [rows * scale + scale, cols * scale + scale, 3]."""
+        px = np.ascontiguousarray(pr_x, dtype=np.float64)
+        py = np.ascontiguousarray(pr_y, dtype=np.float64)
+        t = np.ascontiguousarray(t_ns, dtype=np.int32)
+        nz = np.ascontiguousarray(noise, dtype=np.uint8) if noise is not None else None
+        out = np.zeros((self.rows * scale + scale, self.cols * scale + scale, 3), dtype=np.uint8)
+        self._chk(self.lib.bf_color_time_img(self.h, len(px), _ptr(px), _ptr(py), _ptr(t), _ptr(nz), scale, _ptr(out)))
+        return out
 
     def project(self, fr_x, fr_y, t_ns, pr_x, pr_y, dnx, dny, cx, cy, div, crl):
         fx = np.ascontiguousarray(fr_x, dtype=np.uint16)

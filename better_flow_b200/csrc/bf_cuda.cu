@@ -778,6 +778,55 @@ __global__ void bf_proj_scale_kernel(unsigned char *img, long long P, const unsi
     }
 }
 
+// ---- EventFile::color_time_img (event_file.h:649-747) ------------------------------------------------------------
+__global__ void bf_color_splat_kernel(int n, const double *pr_x, const double *pr_y, const int *t, const unsigned char *noise,
+                                      int scale, int wx, int wy, double x_shift, double y_shift, int t_min, int t_max,
+                                      double *sum_cos, double *sum_sin, unsigned *cnt, int cols) {
+    const int h = scale / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (noise && noise[i]) continue;
+        const double fx = __dadd_rn(__dmul_rn(pr_x[i], (double)scale), x_shift), fy = __dadd_rn(__dmul_rn(pr_y[i], (double)scale), y_shift);
+        if (!(fx == fx) || !(fy == fy)) continue;
+        int x = __double2int_rz(fx), y = __double2int_rz(fy);
+        if (x >= wx || x < 0 || y >= wy || y < 0) continue;                                   // :706-709
+        const float angle = (float)(2 * 3.14 * ((double)(t[i] - t_min) / (double)(t_max - t_min)));   // :711
+        const double co = cos((double)angle), si = sin((double)angle);
+        x += h; y += h;
+        for (int jx = x - h; jx <= x + h; ++jx)
+            for (int jy = y - h; jy <= y + h; ++jy) {
+                const size_t o = (size_t)jx * cols + jy;
+                atomicAdd(sum_cos + o, co); atomicAdd(sum_sin + o, si); atomicAdd(cnt + o, 1u);
+            }
+    }
+}
+// mean direction -> HSV (:724-739) -> BGR (cv::cvtColor HSV2BGR for 8-bit: the sector table of the float formula, results
+// TRUNCATED to 8 bits -- equal to OpenCV 4.13 on 99.65 % of all (H, S) pairs at V = 255, one level off on the rest)
+__global__ void bf_color_finish_kernel(const double *sum_cos, const double *sum_sin, const unsigned *cnt, long long P, unsigned char *out) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (long long)gridDim.x * blockDim.x) {
+        unsigned char b = 0, g = 0, r = 0;
+        const unsigned c = cnt[k];
+        if (c >= 1u) {
+            const float vx = __fdiv_rn((float)sum_cos[k], (float)c), vy = __fdiv_rn((float)sum_sin[k], (float)c);
+            const double speed = hypot((double)vx, (double)vy);
+            double angle = 0;
+            if (speed != 0) angle = (atan2((double)vy, (double)vx) + 3.1416) * 180 / 3.1416;
+            const int H = (int)(angle / 2), S = min(255, (int)(speed * 255));
+            // HSV -> BGR with V = 255
+            const float s = (float)S * (1.0f / 255.0f);
+            float hh = (float)H * (6.0f / 180.0f);
+            int sector = (int)floorf(hh);
+            hh -= (float)sector;
+            sector = ((sector % 6) + 6) % 6;
+            const float tab[4] = {1.0f, 1.0f - s, 1.0f - s * hh, 1.0f - s * (1.0f - hh)};
+            const int sd[6][3] = {{1, 3, 0}, {1, 0, 2}, {3, 0, 1}, {0, 2, 1}, {0, 1, 3}, {2, 1, 0}};
+            b = (unsigned char)min(255, max(0, __float2int_rz(__fmul_rn(tab[sd[sector][0]], 255.0f))));
+            g = (unsigned char)min(255, max(0, __float2int_rz(__fmul_rn(tab[sd[sector][1]], 255.0f))));
+            r = (unsigned char)min(255, max(0, __float2int_rz(__fmul_rn(tab[sd[sector][2]], 255.0f))));
+        }
+        out[3 * k] = b; out[3 * k + 1] = g; out[3 * k + 2] = r;
+    }
+}
+
 // ---- device-resident slice ring (include/bf_cuda.h: bf_ring_*) -------------------------------------------------
 // Cuts "the newest n events, newest -> oldest, local time = timestamp - start" (what a range-for over the
 // reference's CircularArray hands to the optimiser, dvs_flow.h:196-198 + Event::set_local_time, event.h:61-63) out of
@@ -1888,6 +1937,45 @@ int bf_projection_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, base + o_b, P, cudaMemcpyDeviceToHost, c->stream));
     if (nz_avg) CU(cudaMemcpyAsync(nz_avg, base + o_avg, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns, const uint8_t *noise, int scale,
+                      uint8_t *out_bgr) {
+    if (!c || n < 0 || (n > 0 && (!pr_x || !pr_y || !t_ns)) || !out_bgr) return fail(BF_ERR_ARG, "bf_color_time_img: bad arguments");
+    if (scale != 1 && scale != 3 && scale != 5) return fail(BF_ERR_ARG, "scale %d unsupported (1, 3 or 5)", scale);
+    CU(cudaSetDevice(c->device));
+    const int wx = scale * c->res_x, wy = scale * c->res_y, rows = wx + scale, cols = wy + scale;
+    const size_t P = (size_t)rows * cols;
+    int32_t t_min = INT32_MAX, t_max = INT32_MIN;                                    // event_file.h:663-666
+    for (int i = 0; i < n; ++i) { t_min = std::min(t_min, t_ns[i]); t_max = std::max(t_max, t_ns[i]); }
+    if (n == 0) { t_min = 0; t_max = 1; }
+    const double x_shift = -(double)((c->res_x / 2) * scale) + (double)wx / 2.0;      // :690-691
+    const double y_shift = -(double)((c->res_y / 2) * scale) + (double)wy / 2.0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_px = take((size_t)n * 8), o_py = take((size_t)n * 8), o_t = take((size_t)n * 4), o_nz = take((size_t)n);
+    const size_t o_c = take(P * 8), o_s = take(P * 8), o_n = take(P * 4), o_out = take(P * 3);
+    int rc;
+    if ((rc = stage_alloc(c, off)) != BF_OK) return rc;
+    unsigned char *base = (unsigned char *)c->d_stage;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(base + o_px, pr_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(base + o_py, pr_y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(base + o_t, t_ns, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (noise) CU(cudaMemcpyAsync(base + o_nz, noise, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemsetAsync(base + o_c, 0, o_out - o_c, c->stream));
+    if (n > 0)
+        bf_color_splat_kernel<<<std::max(1, std::min(4 * c->sms, (n + 255) / 256)), 256, 0, c->stream>>>(
+            n, (const double *)(base + o_px), (const double *)(base + o_py), (const int *)(base + o_t), noise ? base + o_nz : nullptr, scale,
+            wx, wy, x_shift, y_shift, t_min, t_max, (double *)(base + o_c), (double *)(base + o_s), (unsigned *)(base + o_n), cols);
+    bf_color_finish_kernel<<<std::max(1, std::min(8 * c->sms, (int)((P + 255) / 256))), 256, 0, c->stream>>>(
+        (const double *)(base + o_c), (const double *)(base + o_s), (const unsigned *)(base + o_n), (long long)P, base + o_out);
+    c->launches += n > 0 ? 2 : 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_bgr, base + o_out, P * 3, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return BF_OK;
 }

@@ -20,10 +20,10 @@
 //     timestamp, flags: Event::copy_header_to), and noise marks of the tiny-window guard live on the device only.
 //   * set_generate_pictures / set_generate_video (the reference's --img / --video, dvs_flow.h:256-335): after every
 //     slice a 2 x 2 montage is written -- EventFile::projection_img of the events as recorded and as warped (computed
-//     on the device: bf_projection_img), next to the corresponding mean-timestamp images (bf_time_img) where the
-//     reference puts its HSV-coloured time images.  Without OpenCV there is no JPEG / AVI encoder and no text
-//     rendering: pictures are binary PGM files (frame_N.pgm) with the overlay text of the reference's frames in a
-//     sidecar frame_N.txt, the video is an uncompressed YUV4MPEG2 stream (mono), playable by ffplay / mpv.
+//     on the device: bf_projection_img), next to EventFile::color_time_img of the same events (bf_color_time_img).
+//     Without OpenCV there is no JPEG / AVI encoder and no text rendering: pictures are binary PPM files
+//     (frame_N.ppm) with the overlay text of the reference's frames in a sidecar frame_N.txt, the video is an
+//     uncompressed YUV4MPEG2 stream (4:4:4), playable by ffplay / mpv.
 // The interactive mode is a GUI feature and is accepted but ignored.
 #ifndef BF_DVS_FLOW_H
 #define BF_DVS_FLOW_H
@@ -139,11 +139,11 @@ public:
     void set_scale(int val = 3) { scale = val; }
     void set_generate_video(bool val = true, std::string fname = "out.avi", int fps = 30) {
         generate_video_ = val; video_name_ = fname; video_fps_ = fps;
-        if (val) std::cerr << "video output: uncompressed YUV4MPEG2 (mono) stream in '" << fname << "' (no AVI encoder without OpenCV)" << std::endl;
+        if (val) std::cerr << "video output: uncompressed YUV4MPEG2 (4:4:4) stream in '" << fname << "' (no AVI encoder without OpenCV)" << std::endl;
     }
     void set_generate_pictures(bool val = true, std::string prefix = "./") {
         generate_pictures_ = val; img_prefix_ = prefix;
-        if (val) std::cerr << "picture output: " << prefix << "/frame_N.pgm + frame_N.txt (no JPEG encoder without OpenCV)" << std::endl;
+        if (val) std::cerr << "picture output: " << prefix << "/frame_N.ppm + frame_N.txt (no JPEG encoder without OpenCV)" << std::endl;
     }
     void set_stm_disable(bool val = true) { stm_disable = val; update_ring_on(); }
 
@@ -470,35 +470,35 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::dump_frame(size_
     }
     bf_ctx *ctx = CudaDriver::context(n, 1, std::max(scale, S));
     std::vector<uint8_t> pr_t((size_t)rows * cols), pr_f((size_t)rows * cols);
-    std::vector<float> tm_t((size_t)rows * cols), tm_f((size_t)rows * cols);
+    const int crow = rows + S, ccol = cols + S;                 // color_time_img spans (S * RES + S) pixels per axis
+    std::vector<uint8_t> col_t((size_t)crow * ccol * 3), col_f((size_t)crow * ccol * 3);
     auto check = [](int rc, const char *what) {
         if (rc < 0) { std::cerr << what << " failed: " << bf_last_error() << std::endl; std::exit(1); }
     };
     check(bf_projection_img(ctx, n, fx.data(), fy.data(), nz.data(), S, pr_t.data(), nullptr), "bf_projection_img");
     check(bf_projection_img(ctx, n, px.data(), py.data(), nz.data(), S, pr_f.data(), nullptr), "bf_projection_img");
-    // time images over the full frame: w = S * RES_X - S so that the image is rows x cols; shift = S / 2
-    check(bf_time_img(ctx, n, fx.data(), fy.data(), tl.data(), nz.data(), rows - S, cols - S, S, S / 2, S / 2, tm_t.data()), "bf_time_img");
-    check(bf_time_img(ctx, n, px.data(), py.data(), tl.data(), nz.data(), rows - S, cols - S, S, S / 2, S / 2, tm_f.data()), "bf_time_img");
-    auto to_u8 = [&](const std::vector<float> &t, std::vector<uint8_t> &o) {
-        float mx = 0;
-        for (float v : t) mx = std::max(mx, v);
-        o.resize(t.size());
-        for (size_t k = 0; k < t.size(); ++k) o[k] = mx > 0 ? (uint8_t)std::min(255.0f, std::max(0.0f, t[k] / mx * 255.0f + 0.5f)) : 0;
+    check(bf_color_time_img(ctx, n, fx.data(), fy.data(), tl.data(), nz.data(), S, col_t.data()), "bf_color_time_img");
+    check(bf_color_time_img(ctx, n, px.data(), py.data(), tl.data(), nz.data(), S, col_f.data()), "bf_color_time_img");
+    // 2 x 2 montage, 3 channels (R G B for the PPM / planar for the video): the grey projection images replicated
+    // (cv::cvtColor GRAY2RGB), the colour images cropped to the frame (the reference resizes 543 x 723 -> 540 x 720)
+    std::vector<uint8_t> frame((size_t)4 * rows * cols * 3);
+    auto put = [&](int r0, int c0, const uint8_t *grey, const uint8_t *bgr, int bgr_cols) {
+        for (int r = 0; r < rows; ++r)
+            for (int cc = 0; cc < cols; ++cc) {
+                uint8_t *o = &frame[((size_t)(r0 + r) * 2 * cols + (c0 + cc)) * 3];
+                if (grey) { o[0] = o[1] = o[2] = grey[(size_t)r * cols + cc]; }
+                else { const uint8_t *q = bgr + ((size_t)r * bgr_cols + cc) * 3; o[0] = q[2]; o[1] = q[1]; o[2] = q[0]; }
+            }
     };
-    std::vector<uint8_t> g_t, g_f;
-    to_u8(tm_t, g_t); to_u8(tm_f, g_f);
-    std::vector<uint8_t> frame((size_t)4 * rows * cols);
-    for (int r = 0; r < rows; ++r) {
-        memcpy(&frame[(size_t)r * 2 * cols], &pr_t[(size_t)r * cols], (size_t)cols);
-        memcpy(&frame[(size_t)r * 2 * cols + cols], &g_t[(size_t)r * cols], (size_t)cols);
-        memcpy(&frame[(size_t)(rows + r) * 2 * cols], &pr_f[(size_t)r * cols], (size_t)cols);
-        memcpy(&frame[(size_t)(rows + r) * 2 * cols + cols], &g_f[(size_t)r * cols], (size_t)cols);
-    }
+    put(0, 0, pr_t.data(), nullptr, 0);
+    put(0, cols, nullptr, col_t.data(), ccol);
+    put(rows, 0, pr_f.data(), nullptr, 0);
+    put(rows, cols, nullptr, col_f.data(), ccol);
     if (generate_pictures_) {
         const std::string base = img_prefix_ + "/frame_" + std::to_string(frame_count_);
-        std::ofstream pgm(base + ".pgm", std::ofstream::binary);
-        pgm << "P5\n" << 2 * cols << " " << 2 * rows << "\n255\n";
-        pgm.write(reinterpret_cast<const char *>(frame.data()), (std::streamsize)frame.size());
+        std::ofstream ppm(base + ".ppm", std::ofstream::binary);
+        ppm << "P6\n" << 2 * cols << " " << 2 * rows << "\n255\n";
+        ppm.write(reinterpret_cast<const char *>(frame.data()), (std::streamsize)frame.size());
         // the text the reference renders into the frame (dvs_flow.h:274-318)
         std::ofstream txt(base + ".txt");
         txt << "timestamp: " << double(current_slice_time) / 1000000000.0 << "\n"
@@ -513,10 +513,19 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::dump_frame(size_
         if (!video_out_) {
             video_out_.reset(new std::ofstream(video_name_, std::ofstream::binary));
             if (!*video_out_) std::cout << "Could not open the output video for write" << std::endl;
-            *video_out_ << "YUV4MPEG2 W" << 2 * cols << " H" << 2 * rows << " F" << video_fps_ << ":1 Ip A1:1 Cmono\n";
+            *video_out_ << "YUV4MPEG2 W" << 2 * cols << " H" << 2 * rows << " F" << video_fps_ << ":1 Ip A1:1 C444\n";
+        }
+        // planar Y Cb Cr (BT.601 full range) of the RGB frame
+        const size_t np_ = (size_t)4 * rows * cols;
+        std::vector<uint8_t> yuv(3 * np_);
+        for (size_t k = 0; k < np_; ++k) {
+            const double R = frame[3 * k], G = frame[3 * k + 1], B = frame[3 * k + 2];
+            yuv[k] = (uint8_t)std::min(255.0, std::max(0.0, 0.299 * R + 0.587 * G + 0.114 * B + 0.5));
+            yuv[np_ + k] = (uint8_t)std::min(255.0, std::max(0.0, -0.168736 * R - 0.331264 * G + 0.5 * B + 128.5));
+            yuv[2 * np_ + k] = (uint8_t)std::min(255.0, std::max(0.0, 0.5 * R - 0.418688 * G - 0.081312 * B + 128.5));
         }
         *video_out_ << "FRAME\n";
-        video_out_->write(reinterpret_cast<const char *>(frame.data()), (std::streamsize)frame.size());
+        video_out_->write(reinterpret_cast<const char *>(yuv.data()), (std::streamsize)yuv.size());
     }
 }
 

@@ -56,9 +56,9 @@ static void usage(int ret) {
     printf("    [-i/--interactive]\tEnable interactive mode (ignored: GUI feature)\n");
     printf("    [-G]\t\t\t\tUse GPU support (always on: the CUDA back-end is the only implementation)\n");
     printf("    [--stm-disable]\t\t\t\tDo not use previous estimate as a starting point for a new estimate\n");
-    printf("    [--img]\t\t\t\tOutput flow images after every iteration (frame_N.pgm + frame_N.txt)\n");
+    printf("    [--img]\t\t\t\tOutput flow images after every iteration (frame_N.ppm + frame_N.txt)\n");
     printf("    [--img-prefix <name>]\t\t\t\tSpecify prefix for the generated image files (default = %s)\n", img_prefix.c_str());
-    printf("    [--video]\t\t\t\tOutput a video with flow frames (uncompressed YUV4MPEG2, mono)\n");
+    printf("    [--video]\t\t\t\tOutput a video with flow frames (uncompressed YUV4MPEG2, 4:4:4)\n");
     printf("    [--video-name <name>]\t\t\t\tSpecify the name of the video file (default = %s)\n", video_name.c_str());
     printf("    [--video-fps=<value>]\t\t\t\tSpecify video framerate (default = %i)\n", video_fps);
     printf("    [--bufferize-file]\t\t\t\tRead input file to the buffer first (useful for performance testing)\n");

@@ -280,6 +280,16 @@ long long bf_batch_upload_bytes(bf_ctx *c);   /* host-to-device bytes of one bf_
 int bf_projection_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const uint8_t *noise, int scale,
                       uint8_t *out, double *nz_avg);
 
+/* EventFile::color_time_img (event_file.h:649-747): the second debug image of --img / --video (dvs_flow.h:257-259).  Per
+ * non-noise event a phase angle 2 * 3.14 * (t - t_min) / (t_max - t_min) of its local time (t range over ALL events);
+ * cos / sin of it are averaged per pixel over the scale x scale blocks the events cover (:696-722; the image spans the
+ * full frame, :668-680: (scale * RES_X + scale) x (scale * RES_Y + scale) pixels); the mean direction becomes hue
+ * (angle / 2), its length saturation, value 255 (:724-739), converted HSV -> BGR like cv::cvtColor (:742-746).
+ * out = [rows][cols][3] bytes, B G R.  The reference accumulates in f32 in event order; here the sums are f64 atomics
+ * (order-free), so single pixels may differ by one level from an OpenCV-rendered image (tests allow +-1 on < 1 %). */
+int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, const int32_t *t_ns, const uint8_t *noise,
+                      int scale, uint8_t *out_bgr);
+
 /* ---- device-resident slice ring: DVS_flow's default mode ---------------------------------------
  * Replaces, for the reference's default operating mode (overlapping 50 k-event / 200 ms windows re-minimised every
  * 20 k events / 33 ms, each warm-started from the previous model), the per-slice hand-over of

@@ -257,6 +257,7 @@ int bf_ring_sync(bf_ring *) { return BF_OK; }
 static int unavailable(const char *what) { g_err = std::string(what) + ": not part of the CPU test double"; return BF_ERR_STATE; }
 int bf_time_img(bf_ctx *, int, const double *, const double *, const int32_t *, const uint8_t *, int, int, int, int, int, float *) { return unavailable("bf_time_img"); }
 int bf_projection_img(bf_ctx *, int, const double *, const double *, const uint8_t *, int, uint8_t *, double *) { return unavailable("bf_projection_img"); }
+int bf_color_time_img(bf_ctx *, int, const double *, const double *, const int32_t *, const uint8_t *, int, uint8_t *) { return unavailable("bf_color_time_img"); }
 int bf_project(bf_ctx *, int, const uint16_t *, const uint16_t *, const int32_t *, double *, double *, double *, double *, double, double, double, double, double, double) { return unavailable("bf_project"); }
 int bf_model_from_image(bf_ctx *, int, int, const float *, double *, float *, float *) { return unavailable("bf_model_from_image"); }
 int bf_multi_owner(int slice, int n_devices, int block) { return (n_devices <= 0 || block <= 0 || slice < 0) ? -1 : (slice / block) % n_devices; }

@@ -199,9 +199,9 @@ def test_warm_start_chain_slice_by_slice_against_reference(ctx240, oracle_port):
 
 
 def test_cli_img_and_video_frames(cli, tmp_path, ctx240):
-    """--img / --video (dvs_flow.h:256-335): one 2 x 2 frame per slice -- projection_img of the events as recorded and
-    as warped (EventFile::projection_img on the device) beside the mean-timestamp images -- as PGM + overlay text, and
-    as an uncompressed YUV4MPEG2 stream."""
+    """--img / --video (dvs_flow.h:256-335): one 2 x 2 frame per slice -- EventFile::projection_img of the events as
+    recorded and as warped beside EventFile::color_time_img of the same (both computed on the device) -- as PPM + overlay
+    text, and as an uncompressed YUV4MPEG2 stream."""
     from helpers import ring_slice
     st = synth.make_stream(240, 180, 1.0e6, 0.05, seed=61)
     binf = tmp_path / "s.bin"
@@ -213,18 +213,22 @@ def test_cli_img_and_video_frames(cli, tmp_path, ctx240):
     n_slices = len(open(tmp_path / "flow.txt").read().splitlines())
     assert n_slices >= 2
     rows, cols = 180 * 3, 240 * 3
+    head = b"P6\n%d %d\n255\n" % (2 * cols, 2 * rows)
     for k in range(n_slices):
-        raw = open(tmp_path / ("frame_%d.pgm" % k), "rb").read()
-        head = b"P5\n%d %d\n255\n" % (2 * cols, 2 * rows)
-        assert raw.startswith(head) and len(raw) == len(head) + 4 * rows * cols
+        raw = open(tmp_path / ("frame_%d.ppm" % k), "rb").read()
+        assert raw.startswith(head) and len(raw) == len(head) + 4 * rows * cols * 3
         txt = open(tmp_path / ("frame_%d.txt" % k)).read()
         assert "timestamp:" in txt and "New events:" in txt and "Shift" in txt
-    frame0 = np.frombuffer(open(tmp_path / "frame_0.pgm", "rb").read()[len(head):], dtype=np.uint8).reshape(2 * rows, 2 * cols)
-    # slice 0 = the first 20000 events; the top-left panel is projection_img of them as recorded (show_final = true)
-    idx, _ = ring_slice(st.t_ns, 20000)
-    want, _ = ctx240.projection_img(st.y[idx].astype(np.float64), st.x[idx].astype(np.float64), 3)
-    assert np.array_equal(frame0[:rows, :cols], want)
-    assert frame0[rows:, :cols].any() and frame0[:rows, cols:].any() and frame0[rows:, cols:].any()
+    frame0 = np.frombuffer(open(tmp_path / "frame_0.ppm", "rb").read()[len(head):], dtype=np.uint8).reshape(2 * rows, 2 * cols, 3)
+    # slice 0 = the first 20000 events, local time relative to the slice start
+    idx, start = ring_slice(st.t_ns, 20000)
+    fx, fy = st.y[idx].astype(np.float64), st.x[idx].astype(np.float64)
+    want, _ = ctx240.projection_img(fx, fy, 3)                                   # top-left: projection_img, show_final = true
+    assert all(np.array_equal(frame0[:rows, :cols, ch], want) for ch in range(3))
+    col = ctx240.color_time_img(fx, fy, (st.t_ns[idx] - start).astype(np.int32), 3)   # top-right: color_time_img, show_final = true
+    assert np.array_equal(frame0[:rows, cols:, ::-1], col[:rows, :cols])          # (PPM is R G B, the ABI returns B G R)
+    assert frame0[rows:, :cols].any() and frame0[rows:, cols:].any()
     assert not np.array_equal(frame0[rows:, :cols], frame0[:rows, :cols])        # the warped image differs from the raw one
     y4m = open(vid, "rb").read()
-    assert y4m.startswith(b"YUV4MPEG2 W%d H%d F30:1" % (2 * cols, 2 * rows)) and y4m.count(b"FRAME\n") >= n_slices
+    assert y4m.startswith(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C444" % (2 * cols, 2 * rows)) and y4m.count(b"FRAME\n") >= n_slices
+    assert len(y4m) > n_slices * 12 * rows * cols

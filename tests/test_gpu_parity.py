@@ -412,3 +412,26 @@ def test_projection_img_equals_opencv_golden(ctx240, scale):
         assert np.array_equal(img, want), (name, scale, int(np.sum(img != want)))
     empty, avg = ctx240.projection_img(np.zeros(0), np.zeros(0), scale)
     assert avg == 0 and not empty.any()
+
+
+@pytest.mark.parametrize("scale", [1, 3])
+def test_color_time_img_matches_opencv_golden(ctx240, scale):
+    """bf_color_time_img (EventFile::color_time_img, event_file.h:649-747) against fixtures rendered with the reference's
+    arithmetic in numpy (f32 accumulation in event order) and the REAL cv2.cvtColor(HSV2BGR): the occupancy pattern is
+    identical, colours equal on > 94 % of the occupied pixels (measured 94.8-95.3 % at scale 1, 98.3-98.6 % at scale 3) and
+    within one level on > 99.9 % (order-free
+    f64 accumulation instead of f32 in event order moves a hue / saturation across an 8-bit truncation boundary now and
+    then; OpenCV's own 8-bit HSV conversion differs from the float formula on 0.35 % of all (H, S) pairs)."""
+    import os
+    from oracle import make_golden_img as mg
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "projection_img.npz"))
+    for name, (px, py, nz) in mg.cases().items():
+        t = np.linspace(0, 19_999_999, len(px)).astype(np.int64)
+        got = ctx240.color_time_img(px, py, t, scale, noise=nz)
+        want = G["%s_color_s%d" % (name, scale)]
+        assert got.shape == want.shape
+        assert np.array_equal(got.sum(2) > 0, want.sum(2) > 0)                       # same occupied pixels (V = 255 there)
+        d = np.abs(got.astype(int) - want.astype(int)).max(2)
+        occupied = want.sum(2) > 0
+        assert (d[occupied] == 0).mean() > 0.94, (name, scale, (d[occupied] == 0).mean())
+        assert (d[occupied] <= 1).mean() > 0.999 and d.max() <= 6, (name, scale, d.max(), (d[occupied] <= 1).mean())
