@@ -211,7 +211,7 @@ def class_surface_e2e(device_index):
             binf = os.path.join(d, "stream.bin")
             rec.tofile(binf)
             out = {}
-            for key, extra in (("default_mode", []), ("default_mode_host_ring", ["--no-device-ring"]), ("stm_disable", ["--stm-disable"])):
+            for key, extra in (("default_mode", []), ("default_mode_host_ring", ["--no-device-ring"])):
                 best = None
                 for _ in range(2):
                     r = subprocess.run([cli, "--quiet", "--device=%d" % device_index] + extra + [binf], capture_output=True, text=True,
