@@ -545,6 +545,8 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
         }
     };
     const long long cap = (long long)ev_buffer.capacity();
+    // a request that re-creates the pooled context destroys the ring: read the outstanding models back first
+    if (ring_ && ring_gen_ == CudaDriver::generation() && !CudaDriver::fits(cap + 64, 1, scale)) resolve_deferred();
     bf_ctx *ctx = CudaDriver::context(cap + 64, 1, scale);
     if (!ring_ || ring_gen_ != CudaDriver::generation()) {
         // (a context re-created for more capacity took its rings with it)
@@ -559,7 +561,6 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
             r.fr_x = (uint16_t)e.fr_x; r.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = e.timestamp;
             ring_new_.push_back(r);
         }
-        for (auto &d : deferred_) (void)d;   // (tickets of a destroyed ring cannot be outstanding: resolve_deferred runs before a re-creation can be seen)
     }
     const auto tp0 = std::chrono::steady_clock::now();
     check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
@@ -583,6 +584,11 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
 }
 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::resolve_deferred() {
+    if (!deferred_.empty() && ring_gen_ != CudaDriver::generation()) {
+        // another user of the pooled context re-created it (and with it the ring) while slices were outstanding
+        std::cerr << "DVS_flow: the CUDA context was re-created with " << deferred_.size() << " slices outstanding; their models are lost" << std::endl;
+        std::exit(1);
+    }
     while (!deferred_.empty()) {
         Deferred d = deferred_.front();
         deferred_.pop_front();

@@ -33,6 +33,13 @@ public:
         enabled_ref() = true;
     }
 
+    // Would context(need...) return the existing context?  (Callers that hold objects tied to it -- a bf_ring with
+    // outstanding tickets -- settle them before a request that re-creates the context.)
+    static bool fits(long long need_events, int need_slices, int need_scale) {
+        State &s = state();
+        return s.ctx && s.rows == RES_X && s.cols == RES_Y && need_events <= s.events && need_slices <= s.slices && need_scale <= s.scale;
+    }
+
     // One pooled context per process (the reference re-allocates device buffers for every slice,
     // accel_lib.h:71-145 via dvs_flow.h:210).  Re-created only if a caller needs more capacity.
     static bf_ctx *context(long long need_events, int need_slices, int need_scale) {
