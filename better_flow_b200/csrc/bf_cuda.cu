@@ -1643,7 +1643,7 @@ static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
         CU(cudaLaunchKernelEx(&cfg, bf_minimize_kernel<2, false, true>, P, c->tmaps));
     } else
     CU(cudaLaunchCooperativeKernel(kern, dim3(c->n_groups * c->G), dim3(BF_NT), args, smem_bytes_min(c), c->stream));
-    CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this)
+    if (c->ev_buf[1]) CU(cudaEventRecord(c->ev_free[c->cur], c->stream));   // (a later streamed upload into this event buffer waits for this; no second buffer = no streamed upload yet)
     c->launches += 1;
     return BF_OK;
 }
@@ -1995,8 +1995,8 @@ struct bf_ring {
     SliceDesc *d_desc = nullptr;        // [max_pending]
     bf_slice_result *d_res = nullptr;   // [max_pending + 1]: slot max_pending is the all-zero record (last_model of a fresh DVS_flow)
     bf_slice_result *h_res = nullptr;   // pinned [max_pending]
-    std::vector<cudaEvent_t> done;
     int next_ticket = 0;
+    int fetched_end = 0;                // tickets below this are in h_res
     int prev_slot = -1;
     long long prev_lo = 0, prev_hi = 0;
 };
@@ -2019,8 +2019,6 @@ bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
     ok(cudaMalloc(&r->d_res, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
     ok(cudaMemset(r->d_res, 0, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
     ok(cudaMallocHost(&r->h_res, (size_t)max_pending * sizeof(bf_slice_result)));
-    r->done.resize((size_t)max_pending, nullptr);
-    for (auto &ev : r->done) ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     r->pushes.resize(16);
     for (auto &p : r->pushes) { p.ev = nullptr; p.lo = p.hi = 0; p.open = false; ok(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming)); }
     if (e != cudaSuccess) {
@@ -2038,7 +2036,6 @@ void bf_ring_destroy(bf_ring *r) {
     cudaStreamSynchronize(r->c->stream);
     r->c->rings.erase(std::remove(r->c->rings.begin(), r->c->rings.end(), r), r->c->rings.end());
     cudaFree(r->d_ring); cudaFreeHost(r->h_stage); cudaFree(r->d_desc); cudaFree(r->d_res); cudaFreeHost(r->h_res);
-    for (auto ev : r->done) if (ev) cudaEventDestroy(ev);
     for (auto &p : r->pushes) if (p.ev) cudaEventDestroy(p.ev);
     delete r;
 }
@@ -2050,9 +2047,6 @@ int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
     bf_ctx *c = r->c;
     CU(cudaSetDevice(c->device));
     if (n > r->cap) { ev += n - r->cap; r->pushed += n - r->cap; n = (int)r->cap; }   // only the newest `cap` can ever be used
-    unsigned bad = 0;
-    for (int i = 0; i < n; ++i) bad |= (unsigned)((int)ev[i].fr_x >= c->res_x) | (unsigned)((int)(ev[i].fr_y & 0x7fffu) >= c->res_y);
-    if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
     int done_n = 0;
     while (done_n < n) {
         // one piece = contiguous both in the staging ring and in the device ring
@@ -2061,7 +2055,19 @@ int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
         // the staging entries must not be rewritten while an earlier copy may still be reading them
         for (auto &p : r->pushes)
             if (p.open && p.lo < s_off + piece && s_off < p.hi) { CU(cudaEventSynchronize(p.ev)); p.open = false; }
-        memcpy(r->h_stage + s_off, ev + done_n, (size_t)piece * sizeof(bf_ring_event));
+        // one pass: copy into the pinned staging ring and check the coordinates against the sensor
+        unsigned bad = 0;
+        {
+            bf_ring_event *dst = r->h_stage + s_off;
+            const bf_ring_event *src = ev + done_n;
+            const unsigned rx = (unsigned)c->res_x, ry = (unsigned)c->res_y;
+            for (int i = 0; i < piece; ++i) {
+                const bf_ring_event e = src[i];
+                bad |= (unsigned)(e.fr_x >= rx) | (unsigned)((e.fr_y & 0x7fffu) >= ry);
+                dst[i] = e;
+            }
+        }
+        if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
         CU(cudaMemcpyAsync(r->d_ring + d_off, r->h_stage + s_off, (size_t)piece * sizeof(bf_ring_event), cudaMemcpyHostToDevice, c->stream));
         bf_ring::Push &p = r->pushes[r->push_next++ % r->pushes.size()];
         if (p.open) CU(cudaEventSynchronize(p.ev));
@@ -2092,8 +2098,7 @@ int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_it
     L.cluster = c->ring_cluster;
     const int rc = launch_spec(c, L);
     if (rc != BF_OK) return rc;
-    CU(cudaMemcpyAsync(r->h_res + slot, r->d_res + slot, sizeof(bf_slice_result), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaEventRecord(r->done[(size_t)slot], c->stream));
+    // (the record stays on the device -- the next slice of a chain reads it there; bf_ring_result fetches on demand)
     r->prev_slot = slot; r->prev_lo = r->pushed - n; r->prev_hi = r->pushed;
     return ticket;
 }
@@ -2102,7 +2107,13 @@ int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out) {
     if (!r || !out || ticket < 0 || ticket >= r->next_ticket || ticket < r->next_ticket - r->max_pending)
         return fail(BF_ERR_ARG, "bf_ring_result: ticket %d is not (or no longer) available", ticket);
     const int slot = ticket % r->max_pending;
-    CU(cudaEventSynchronize(r->done[(size_t)slot]));
+    if (ticket >= r->fetched_end) {
+        // one copy of the whole (small) record array behind everything enqueued so far, then wait for it
+        CU(cudaSetDevice(r->c->device));
+        CU(cudaMemcpyAsync(r->h_res, r->d_res, (size_t)r->max_pending * sizeof(bf_slice_result), cudaMemcpyDeviceToHost, r->c->stream));
+        CU(cudaStreamSynchronize(r->c->stream));
+        r->fetched_end = r->next_ticket;
+    }
     *out = r->h_res[slot];
     return BF_OK;
 }

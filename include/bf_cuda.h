@@ -306,8 +306,9 @@ int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, 
  *                   result record, so the call returns without waiting for that slice: a whole warm-start chain is
  *                   stream-ordered device work and the host only enqueues.  The tiny-window guard's noise marking
  *                   (optimizer_rolling.h:49-55) is applied to the ring entries on the device as well.
- *   bf_ring_result  waits for one slice and returns its record (tickets are results of bf_ring_slice, in order;
- *                   a ticket stays readable until `max_pending` later slices have been enqueued).
+ *   bf_ring_result  returns the record of one slice (tickets are results of bf_ring_slice, in order; a ticket stays
+ *                   readable until `max_pending` later slices have been enqueued).  Records are fetched on demand: the
+ *                   first request for a ticket that has not been fetched yet waits for everything enqueued so far.
  * A ring belongs to one context and shares its stream, event buffer and images with the batch entry points (calls
  * are serialised in stream order).  Per-event outputs are not available through the ring (use bf_minimize). */
 typedef struct bf_ring bf_ring;
