@@ -66,7 +66,7 @@ ABI_SYMBOLS = (
     "bf_multi_reset", "bf_multi_add_packed", "bf_multi_run", "bf_multi_sync", "bf_multi_size", "bf_multi_result",
     "bf_multi_locate", "bf_multi_launch_count",
     "bf_projection_img", "bf_color_time_img", "bf_batch_add_delta", "bf_batch_upload_bytes",
-    "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed",
+    "bf_ring_create", "bf_ring_destroy", "bf_ring_push", "bf_ring_slice", "bf_ring_result", "bf_ring_sync", "bf_ring_pushed", "bf_ring_seed", "bf_ring_reserve", "bf_ring_commit",
 )
 
 _lib = None
@@ -150,6 +150,9 @@ def load() -> C.CDLL:
         lib.bf_ring_slice.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
         lib.bf_ring_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(SliceResult)]
         lib.bf_ring_sync.argtypes = [C.c_void_p]
+        lib.bf_ring_reserve.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.bf_ring_commit.argtypes = [C.c_void_p, C.c_int]
+        lib.bf_ring_seed.argtypes = [C.c_void_p, C.POINTER(Model)]
         lib.bf_ring_pushed.argtypes = [C.c_void_p]
         lib.bf_ring_pushed.restype = C.c_longlong
         assert C.sizeof(SliceResult) == RESULT_BYTES and C.sizeof(Model) == 88
@@ -450,6 +453,16 @@ class Ring:
         ev["fr_x"], ev["fr_y"], ev["timestamp"] = fr_x, fr_y, timestamp_ns
         self._chk(self.lib.bf_ring_push(self.h, _ptr(ev), len(ev)))
 
+    def push_in_place(self, fr_x, fr_y, timestamp_ns, reserve=None):
+        """bf_ring_reserve / bf_ring_commit: the events are written straight into the ring's pinned staging buffer."""
+        n = len(fr_x)
+        where = C.c_void_p()
+        self._chk(self.lib.bf_ring_reserve(self.h, int(reserve or max(n, 1)), C.byref(where)))
+        ev = np.ctypeslib.as_array(C.cast(where, C.POINTER(C.c_uint8)), shape=(n * RING_EVENT_DTYPE.itemsize,)).view(RING_EVENT_DTYPE) if n else None
+        if n:
+            ev["fr_x"], ev["fr_y"], ev["reserved"], ev["timestamp"] = fr_x, fr_y, 0, timestamp_ns
+        self._chk(self.lib.bf_ring_commit(self.h, n))
+
     def slice(self, n, slice_start, scale=3, max_iter=-1, chain=True) -> int:
         return self._chk(self.lib.bf_ring_slice(self.h, int(n), int(slice_start), scale, max_iter, 1 if chain else 0))
 
@@ -460,6 +473,10 @@ class Ring:
 
     def sync(self):
         self._chk(self.lib.bf_ring_sync(self.h))
+
+    def seed(self, model):
+        """The model the next chained slice starts from (11 values as Model.as_array returns them)."""
+        self._chk(self.lib.bf_ring_seed(self.h, C.byref(Model.from_array(model))))
 
     @property
     def pushed(self):

@@ -1988,6 +1988,7 @@ struct bf_ring {
     bf_ring_event *d_ring = nullptr;
     bf_ring_event *h_stage = nullptr;   // pinned staging ring, `stage_cap` entries
     long long stage_cap = 0, stage_pos = 0;
+    long long res_off = 0; int res_n = 0;   // the open reservation (bf_ring_reserve), res_n = 0: none
     struct Push { cudaEvent_t ev; long long lo, hi; bool open; };
     std::vector<Push> pushes;           // the last copies issued from the staging ring
     size_t push_next = 0;
@@ -2042,38 +2043,74 @@ void bf_ring_destroy(bf_ring *r) {
 
 long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
 
+// Waits until no earlier copy still reads staging entries [lo, hi).
+static int ring_stage_wait(bf_ring *r, long long lo, long long hi) {
+    for (auto &p : r->pushes)
+        if (p.open && p.lo < hi && lo < p.hi) { CU(cudaEventSynchronize(p.ev)); p.open = false; }
+    return BF_OK;
+}
+
+// Checks staging entries [s_off, s_off + n) against the sensor and enqueues their copy to the device ring (the part of
+// the device ring they land in may wrap: two copies then); one tracking entry for the whole range.
+static int ring_stage_send(bf_ring *r, long long s_off, int n) {
+    bf_ctx *c = r->c;
+    const bf_ring_event *src = r->h_stage + s_off;
+    const unsigned rx = (unsigned)c->res_x, ry = (unsigned)c->res_y;
+    unsigned bad = 0;
+    for (int i = 0; i < n; ++i) bad |= (unsigned)(src[i].fr_x >= rx) | (unsigned)((src[i].fr_y & 0x7fffu) >= ry);
+    if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
+    int skip = 0;
+    if (n > r->cap) { skip = n - (int)r->cap; r->pushed += skip; }   // only the newest `cap` can ever be used
+    for (int done_n = skip; done_n < n;) {
+        const long long d_off = r->pushed % r->cap;
+        const int piece = (int)std::min<long long>(n - done_n, r->cap - d_off);
+        CU(cudaMemcpyAsync(r->d_ring + d_off, src + done_n, (size_t)piece * sizeof(bf_ring_event), cudaMemcpyHostToDevice, c->stream));
+        r->pushed += piece; done_n += piece;
+    }
+    bf_ring::Push &p = r->pushes[r->push_next++ % r->pushes.size()];
+    if (p.open) CU(cudaEventSynchronize(p.ev));
+    p.lo = s_off; p.hi = s_off + n; p.open = true;
+    CU(cudaEventRecord(p.ev, c->stream));
+    return BF_OK;
+}
+
+int bf_ring_reserve(bf_ring *r, int n, bf_ring_event **where) {
+    if (!r || !where || n <= 0 || n > r->stage_cap / 2) return fail(BF_ERR_ARG, "bf_ring_reserve: n must be in 1 .. %lld", r ? r->stage_cap / 2 : 0LL);
+    CU(cudaSetDevice(r->c->device));
+    long long s_off = r->stage_pos % r->stage_cap;
+    if (s_off + n > r->stage_cap) { r->stage_pos += r->stage_cap - s_off; s_off = 0; }   // contiguous room: skip the tail
+    const int rc = ring_stage_wait(r, s_off, s_off + n);
+    if (rc != BF_OK) return rc;
+    r->res_off = s_off; r->res_n = n;
+    *where = r->h_stage + s_off;
+    return BF_OK;
+}
+
+int bf_ring_commit(bf_ring *r, int n) {
+    if (!r || n < 0 || n > r->res_n) return fail(BF_ERR_ARG, "bf_ring_commit: n exceeds the reservation");
+    CU(cudaSetDevice(r->c->device));
+    if (n > 0) {
+        const int rc = ring_stage_send(r, r->res_off, n);
+        if (rc != BF_OK) return rc;
+        r->stage_pos += n;
+    }
+    r->res_n = 0;
+    return BF_OK;
+}
+
 int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
     if (!r || n < 0 || (n > 0 && !ev)) return fail(BF_ERR_ARG, "bf_ring_push: bad arguments");
-    bf_ctx *c = r->c;
-    CU(cudaSetDevice(c->device));
+    if (r->res_n > 0) return fail(BF_ERR_STATE, "bf_ring_push: a reservation is open (bf_ring_commit first)");
+    const int chunk_max = (int)std::min<long long>(r->stage_cap / 2, 1 << 20);
     if (n > r->cap) { ev += n - r->cap; r->pushed += n - r->cap; n = (int)r->cap; }   // only the newest `cap` can ever be used
-    int done_n = 0;
-    while (done_n < n) {
-        // one piece = contiguous both in the staging ring and in the device ring
-        const long long s_off = r->stage_pos % r->stage_cap, d_off = r->pushed % r->cap;
-        const int piece = (int)std::min<long long>(std::min<long long>(n - done_n, r->stage_cap - s_off), r->cap - d_off);
-        // the staging entries must not be rewritten while an earlier copy may still be reading them
-        for (auto &p : r->pushes)
-            if (p.open && p.lo < s_off + piece && s_off < p.hi) { CU(cudaEventSynchronize(p.ev)); p.open = false; }
-        // one pass: copy into the pinned staging ring and check the coordinates against the sensor
-        unsigned bad = 0;
-        {
-            bf_ring_event *dst = r->h_stage + s_off;
-            const bf_ring_event *src = ev + done_n;
-            const unsigned rx = (unsigned)c->res_x, ry = (unsigned)c->res_y;
-            for (int i = 0; i < piece; ++i) {
-                const bf_ring_event e = src[i];
-                bad |= (unsigned)(e.fr_x >= rx) | (unsigned)((e.fr_y & 0x7fffu) >= ry);
-                dst[i] = e;
-            }
-        }
-        if (bad) return fail(BF_ERR_ARG, "event outside the %dx%d sensor", c->res_x, c->res_y);
-        CU(cudaMemcpyAsync(r->d_ring + d_off, r->h_stage + s_off, (size_t)piece * sizeof(bf_ring_event), cudaMemcpyHostToDevice, c->stream));
-        bf_ring::Push &p = r->pushes[r->push_next++ % r->pushes.size()];
-        if (p.open) CU(cudaEventSynchronize(p.ev));
-        p.lo = s_off; p.hi = s_off + piece; p.open = true;
-        CU(cudaEventRecord(p.ev, c->stream));
-        r->stage_pos += piece; r->pushed += piece; done_n += piece;
+    for (int done_n = 0; done_n < n;) {
+        const int piece = std::min(n - done_n, chunk_max);
+        bf_ring_event *dst = nullptr;
+        int rc = bf_ring_reserve(r, piece, &dst);
+        if (rc != BF_OK) return rc;
+        std::memcpy(dst, ev + done_n, (size_t)piece * sizeof(bf_ring_event));
+        if ((rc = bf_ring_commit(r, piece)) != BF_OK) { r->res_n = 0; return rc; }
+        done_n += piece;
     }
     return BF_OK;
 }
@@ -2101,6 +2138,19 @@ int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_it
     // (the record stays on the device -- the next slice of a chain reads it there; bf_ring_result fetches on demand)
     r->prev_slot = slot; r->prev_lo = r->pushed - n; r->prev_hi = r->pushed;
     return ticket;
+}
+
+int bf_ring_seed(bf_ring *r, const bf_model *model) {
+    if (!r || !model) return fail(BF_ERR_ARG, "bf_ring_seed: bad arguments");
+    CU(cudaSetDevice(r->c->device));
+    // the spare record behind the `max_pending` result slots is what the first slice of a chain reads (all zero after
+    // bf_ring_create = set_model(ObjectModel())); the copy is ordered behind the slices already enqueued
+    bf_slice_result rec;
+    std::memset(&rec, 0, sizeof rec);
+    rec.model = *model;
+    CU(cudaMemcpyAsync(r->d_res + r->max_pending, &rec, sizeof rec, cudaMemcpyHostToDevice, r->c->stream));   // pageable source: staged before the call returns
+    r->prev_slot = -1;
+    return BF_OK;
 }
 
 int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out) {

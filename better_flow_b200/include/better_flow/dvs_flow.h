@@ -16,8 +16,10 @@
 //   * set_device_ring(): keep the slice ring on the device (bf_ring_*): only new events are uploaded, a slice is an
 //     index range, and the warm-start chain is stream-ordered device work -- the host enqueues slices and reads the
 //     models back later (at once when the per-slice dump is printed).  Used when no per-event state is wanted
-//     (set_lazy_events, no accumulation); `ev_buffer` then maintains only the identity of its events (coordinates,
-//     timestamp, flags: Event::copy_header_to), and noise marks of the tiny-window guard live on the device only.
+//     (set_lazy_events, no accumulation).  The host then only has to know WHICH events the window holds (triggers,
+//     eviction, slice start, a rebuild of the device ring): they are kept as 16-byte records in a ring of the same
+//     capacity / span / quirks (`hdr_buffer_`) and `ev_buffer` stays empty; noise marks of the tiny-window guard live
+//     on the device only.  Switching the mode with events in the window moves them across.
 //   * set_generate_pictures / set_generate_video (the reference's --img / --video, dvs_flow.h:256-335): after every
 //     slice a 2 x 2 montage is written -- EventFile::projection_img of the events as recorded and as warped (computed
 //     on the device: bf_projection_img), next to EventFile::color_time_img of the same events (bf_color_time_img).
@@ -96,11 +98,39 @@ protected:
     // device-resident ring (set_device_ring)
     bool device_ring_ = false;
     bool ring_on_ = false;                   // device_ring_active(), re-evaluated by every setter it depends on
-    void update_ring_on() { ring_on_ = device_ring_ && lazy_events_ && !accumulate && !local_ && gpus_ == 1 && !(batch_ > 1 && stm_disable); }
+    // The window as the device ring's own 16-byte records (noise = bit 15 of fr_y, as on the device).
+    struct RingHeader : bf_ring_event {
+        sll operator-(const RingHeader &rhs) const { return sll(timestamp) - sll(rhs.timestamp); }   // Event::operator-
+        void copy_header_to(RingHeader &o) const { o = *this; }
+    };
+    static RingHeader header_of(const Event &e) {
+        RingHeader r;
+        r.fr_x = (uint16_t)e.fr_x; r.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = e.timestamp;
+        return r;
+    }
+    static_assert(sizeof(RingHeader) == sizeof(bf_ring_event), "RingHeader adds no data");
+    RingCore<RingHeader> hdr_buffer_;
+    void update_ring_on() {
+        const bool on = device_ring_ && lazy_events_ && !accumulate && !local_ && gpus_ == 1 && !(batch_ > 1 && stm_disable);
+        if (on != ring_on_) migrate_window(on);
+        ring_on_ = on;
+    }
+    void migrate_window(bool to_headers);
+    // the window, whichever ring holds it
+    size_t win_size() { return ring_on_ ? hdr_buffer_.size() : ev_buffer.size(); }
+    ull win_timestamp(size_t idx) { return ring_on_ ? hdr_buffer_[idx].timestamp : ev_buffer[idx].timestamp; }
     bf_ring *ring_ = nullptr;
     unsigned long ring_gen_ = 0;             // CudaDriver::generation() the ring was created under
     int ring_pending_ = 64;
-    std::vector<bf_ring_event> ring_new_;    // events pushed since the last slice
+    std::vector<RingHeader> ring_new_;       // scratch for a rebuild of the device ring
+    // New events go straight into the device ring's pinned staging buffer (bf_ring_reserve / bf_ring_commit): `stage_`
+    // is the open reservation, valid while the pooled context is the one the ring was created under.
+    bf_ring_event *stage_ = nullptr;
+    int stage_fill_ = 0, stage_room_ = 0;
+    const unsigned long *ctx_gen_ = CudaDriver::generation_ptr();
+    static constexpr int kStageChunk = 32768;
+    __attribute__((noinline)) void stage_slow(const RingHeader &r);
+    void stage_drop() { stage_ = nullptr; stage_fill_ = stage_room_ = 0; }
     struct Deferred { SliceLog log; int ticket; };
     std::deque<Deferred> deferred_;          // slices enqueued on the device whose models have not been read back yet
     double t_push_ = 0, t_slice_ = 0, t_resolve_ = 0;   // host seconds spent in bf_ring_push / bf_ring_slice / bf_ring_result
@@ -114,19 +144,37 @@ public:
         : on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
           scale(3), stm_disable(false), batch_(1), gpus_(1), local_(false), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
-          iters_done_(0) {}
+          iters_done_(0), hdr_buffer_(MAX_SZ, SPAN) {}
 
     // run-time sized variant (CLI flags --max-events / --slice-time)
     DVS_flow(ull on_ev_change_, ull on_time_change_, ull start_time, size_t capacity, sll span)
         : ev_buffer(capacity, span), on_ev_change(on_ev_change_), on_time_change(on_time_change_), time_diff(0), event_diff(0),
           last_slice_time(start_time), current_slice_time(start_time), accumulate(false), manual_mode(false), max_iter(-1),
           scale(3), stm_disable(false), batch_(1), gpus_(1), local_(false), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
-          iters_done_(0) {}
+          iters_done_(0), hdr_buffer_(capacity, span) {}
 
     ~DVS_flow() {}
 
-    bool add_event(Event &ev);
-    void recompute();
+    // The per-event part is small and inlined into the caller's loop; the slice itself is not.
+    __attribute__((always_inline)) inline bool add_event(Event &ev) {
+        if (ring_on_) {
+            // the slices are cut on the device: 16 bytes per event instead of the 152-byte record
+            const RingHeader r = header_of(ev);
+            hdr_buffer_.push_back_header(r);
+            if (stage_fill_ < stage_room_ && *ctx_gen_ == ring_gen_) stage_[stage_fill_++] = r;
+            else stage_slow(r);
+        } else {
+            ev_buffer.push_back(ev);
+        }
+        event_diff++;
+        if (ev.timestamp < current_slice_time) unsorted_ = true;
+        current_slice_time = ev.timestamp;
+        time_diff = current_slice_time - last_slice_time;   // time only increases
+        if ((event_diff < (sll)on_ev_change) && (time_diff < (sll)on_time_change)) return false;
+        recompute();
+        return true;
+    }
+    __attribute__((noinline)) void recompute();
     void flush();   // minimise whatever is still queued (batch mode)
 
     void set_accumulate(bool val = true) { accumulate = val; update_ring_on(); }
@@ -147,7 +195,7 @@ public:
     }
     void set_stm_disable(bool val = true) { stm_disable = val; update_ring_on(); }
 
-    sll get_buf_size() { return ev_buffer.size(); }
+    sll get_buf_size() { return win_size(); }
     sll get_time_diff() { return time_diff; }
     sll get_buf_time_diff() { return current_slice_time - slice_start_time(); }
 
@@ -170,7 +218,7 @@ public:
 protected:
     // dvs_flow.h:186-193: the oldest timestamp when the buffer overflowed, else now - SPAN
     ull slice_start_time() {
-        if (ev_buffer.size() == ev_buffer.capacity()) return ev_buffer[ev_buffer.capacity() - 1].timestamp;
+        if (win_size() == ev_buffer.capacity()) return win_timestamp(ev_buffer.capacity() - 1);
         const ull span = (ull)ev_buffer.span();
         return (current_slice_time > span) ? current_slice_time - span : 0;
     }
@@ -204,25 +252,24 @@ protected:
     void ring_slice(const SliceLog &log, ull start);
 };
 
-template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::add_event(Event &ev) {
-    const bool on_device = device_ring_active();
-    if (on_device) {
-        // the slices are cut on the device: the host ring only has to know WHICH events it holds (triggers, eviction,
-        // slice start, a rebuild of the device ring) -- 26 bytes per event instead of the 152-byte record
-        ev_buffer.push_back_header(ev);
-        bf_ring_event r;
-        r.fr_x = (uint16_t)ev.fr_x; r.fr_y = (uint16_t)(ev.fr_y | (ev.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = ev.timestamp;
-        ring_new_.push_back(r);
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::migrate_window(bool to_headers) {
+    // oldest -> newest, so that the other ring ends up with the same visible content (size, order, full-buffer quirk)
+    resolve_deferred();   // models of slices already enqueued on the device are logged before the mode changes
+    if (ring_ && ring_gen_ == CudaDriver::generation()) bf_ring_destroy(ring_);   // (its content would be stale when the mode comes back)
+    ring_ = nullptr;
+    stage_drop();
+    if (to_headers) {
+        for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) hdr_buffer_.push_back_header(header_of(ev_buffer[i]));
+        ev_buffer = CircularArray<Event, MAX_SZ, SPAN>(ev_buffer.capacity(), ev_buffer.span());
     } else {
-        ev_buffer.push_back(ev);
+        for (long int i = (long int)hdr_buffer_.size() - 1; i >= 0; i--) {
+            const RingHeader &h = hdr_buffer_[i];
+            Event e(h.fr_x, h.fr_y & 0x7fffu, h.timestamp);
+            e.noise = (h.fr_y & BF_EVENT_NOISE) != 0;
+            ev_buffer.push_back(e);
+        }
+        hdr_buffer_ = RingCore<RingHeader>(hdr_buffer_.capacity(), hdr_buffer_.span());
     }
-    event_diff++;
-    if (ev.timestamp < current_slice_time) unsorted_ = true;
-    current_slice_time = ev.timestamp;
-    time_diff = current_slice_time - last_slice_time;   // time only increases
-    if ((event_diff < (sll)on_ev_change) && (time_diff < (sll)on_time_change)) return false;
-    recompute();
-    return true;
 }
 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
@@ -230,11 +277,11 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
 
     // The slice = what a range-for over the buffer visits: newest -> oldest, and SZ-1 elements when the buffer is
     // full (dvs_flow.h:196-198 builds a LinearEventPtrs of exactly these).
-    const size_t held = ev_buffer.size();
+    const size_t held = win_size();
     SliceLog log;
     log.size = held - ((held == ev_buffer.capacity() && held > 0) ? 1 : 0);
-    log.ts_first = log.size ? ev_buffer[0].timestamp : 0;
-    log.ts_last = log.size ? ev_buffer[log.size - 1].timestamp : 0;
+    log.ts_first = log.size ? win_timestamp(0) : 0;
+    log.ts_last = log.size ? win_timestamp(log.size - 1) : 0;
 
     LinearEventPtrs e_ptrs;
     if (local_) {
@@ -534,6 +581,27 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::flush() {
     resolve_deferred();
 }
 
+// The open reservation is full, or there is none (no ring yet, or the pooled context -- and with it the ring and its
+// staging buffer -- was re-created by another user).  Without a ring nothing is lost: the next slice rebuilds the
+// device ring from the window (`hdr_buffer_`).
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::stage_slow(const RingHeader &r) {
+    if (!ring_ || ring_gen_ != CudaDriver::generation()) {
+        stage_drop();
+        return;
+    }
+    auto check = [](int rc, const char *what) {
+        if (rc < 0) {
+            std::cerr << what << " failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+    };
+    check(bf_ring_commit(ring_, stage_fill_), "bf_ring_commit");
+    check(bf_ring_reserve(ring_, kStageChunk, &stage_), "bf_ring_reserve");
+    stage_room_ = kStageChunk;
+    stage_[0] = r;
+    stage_fill_ = 1;
+}
+
 // Default mode on the device-resident ring (include/bf_cuda.h: bf_ring_*).  Per slice the host uploads the events
 // that arrived since the last slice and enqueues "newest n events, local time relative to `start`, warm-started from
 // the previous slice's model ON THE DEVICE"; nothing here waits for the GPU unless the per-slice dump is wanted.
@@ -548,23 +616,26 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
     // a request that re-creates the pooled context destroys the ring: read the outstanding models back first
     if (ring_ && ring_gen_ == CudaDriver::generation() && !CudaDriver::fits(cap + 64, 1, scale)) resolve_deferred();
     bf_ctx *ctx = CudaDriver::context(cap + 64, 1, scale);
+    const auto tp0 = std::chrono::steady_clock::now();
     if (!ring_ || ring_gen_ != CudaDriver::generation()) {
         // (a context re-created for more capacity took its rings with it)
+        stage_drop();
         ring_ = bf_ring_create(ctx, cap, ring_pending_);
         if (!ring_) check(-1, "bf_ring_create");
         ring_gen_ = CudaDriver::generation();
-        // everything the buffer holds, oldest -> newest (the events of this slice included)
+        // a ring created in the middle of a stream continues the warm-start chain from the host's last model
+        const bf_model seed = last_model.to_pod();
+        check(bf_ring_seed(ring_, &seed), "bf_ring_seed");
+        // everything the window holds, oldest -> newest (the events of this slice included)
         ring_new_.clear();
-        for (long int i = (long int)ev_buffer.size() - 1; i >= 0; i--) {
-            const Event &e = ev_buffer[i];
-            bf_ring_event r;
-            r.fr_x = (uint16_t)e.fr_x; r.fr_y = (uint16_t)(e.fr_y | (e.noise ? BF_EVENT_NOISE : 0u)); r.reserved = 0; r.timestamp = e.timestamp;
-            ring_new_.push_back(r);
-        }
+        for (long int i = (long int)hdr_buffer_.size() - 1; i >= 0; i--) ring_new_.push_back(hdr_buffer_[i]);
+        check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
+        ring_new_.clear();
+    } else {
+        check(bf_ring_commit(ring_, stage_fill_), "bf_ring_commit");   // the events that arrived since the last slice
     }
-    const auto tp0 = std::chrono::steady_clock::now();
-    check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
-    ring_new_.clear();
+    check(bf_ring_reserve(ring_, kStageChunk, &stage_), "bf_ring_reserve");
+    stage_fill_ = 0; stage_room_ = kStageChunk;
     const auto tp1 = std::chrono::steady_clock::now();
     t_push_ += std::chrono::duration<double>(tp1 - tp0).count();
     if (log.size > 0) {

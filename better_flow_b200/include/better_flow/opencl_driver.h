@@ -95,6 +95,7 @@ public:
 
     // bumped whenever the pooled context is (re)created: objects tied to the old context (bf_ring) are gone then
     static unsigned long generation() { return state().generation; }
+    static const unsigned long *generation_ptr() { return &state().generation; }   // (for per-event checks)
 
     static void shutdown() {
         State &s = state();

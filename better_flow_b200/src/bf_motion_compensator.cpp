@@ -84,7 +84,8 @@ static void usage(int ret) {
     exit(ret);
 }
 
-int main(int argc, char *argv[]) {
+// (GCC treats `main` itself as cold code -- run once -- and inlines nothing into it; the per-event loop lives here.)
+__attribute__((hot)) static int tool_main(int argc, char *argv[]) {
     if (argc == 1) usage(1);
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--help")) usage(0);
@@ -276,3 +277,5 @@ int main(int argc, char *argv[]) {
     stamp("shutdown");
     return 0;
 }
+
+int main(int argc, char *argv[]) { return tool_main(argc, argv); }

@@ -298,6 +298,9 @@ int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, 
  * re-upload the 60-95 % of the window it already sent for the previous slice (accel_lib.h:83-124 uploads per
  * optimiser instance).  Here the ring lives on the device:
  *   bf_ring_push    appends only the NEW events (absolute timestamps, 16-byte records) -- asynchronous H2D;
+ *   bf_ring_reserve / bf_ring_commit   the same without the staging copy: `reserve` hands out room for up to n events
+ *                   in the ring's pinned staging buffer (waiting for earlier copies that still read that part), the
+ *                   caller writes its events there as they arrive, `commit(m <= n)` checks and sends the first m;
  *   bf_ring_slice   enqueues "minimise the newest n events, local time = timestamp - slice_start"
  *                   (OptimizerRolling::set_cloud / set_time / [set_model] / run, optimizer_rolling.h:236-299,48-125):
  *                   a small kernel cuts the packed newest->oldest slice out of the ring (the order of
@@ -309,6 +312,10 @@ int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, 
  *   bf_ring_result  returns the record of one slice (tickets are results of bf_ring_slice, in order; a ticket stays
  *                   readable until `max_pending` later slices have been enqueued).  Records are fetched on demand: the
  *                   first request for a ticket that has not been fetched yet waits for everything enqueued so far.
+ *   bf_ring_seed    sets the model the NEXT chained slice starts from (the caller's last_model when a ring is created
+ *                   in the middle of a stream -- after a context was re-created, or when the host path handled the
+ *                   slices before); without it the first chained slice starts from ObjectModel().  The noise marks of
+ *                   the slice before are not carried over.
  * A ring belongs to one context and shares its stream, event buffer and images with the batch entry points (calls
  * are serialised in stream order).  Per-event outputs are not available through the ring (use bf_minimize). */
 typedef struct bf_ring bf_ring;
@@ -320,8 +327,11 @@ typedef struct bf_ring_event {
 bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending);
 void bf_ring_destroy(bf_ring *r);
 int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n);
+int bf_ring_reserve(bf_ring *r, int n, bf_ring_event **where);   /* n <= capacity */
+int bf_ring_commit(bf_ring *r, int n);
 int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain);   /* -> ticket */
 int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out);
+int bf_ring_seed(bf_ring *r, const bf_model *model);
 int bf_ring_sync(bf_ring *r);
 long long bf_ring_pushed(bf_ring *r);   /* events appended so far */
 

@@ -191,6 +191,8 @@ struct bf_ring {
     bool have_prev = false;
     bf_slice_result prev;
     long long prev_lo = 0, prev_hi = 0;
+    std::vector<bf_ring_event> stage;     // bf_ring_reserve / bf_ring_commit
+    int res_n = 0;
 };
 static long long g_ring_pushes = 0, g_ring_slices = 0;
 extern "C" {
@@ -217,6 +219,18 @@ int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
     }
     g_ring_pushes += n;
     return BF_OK;
+}
+int bf_ring_reserve(bf_ring *r, int n, bf_ring_event **where) {
+    if (!r || !where || n <= 0) { g_err = "bf_ring_reserve: bad arguments"; return BF_ERR_ARG; }
+    if (r->stage.size() < (size_t)n) r->stage.resize((size_t)n);
+    r->res_n = n;
+    *where = r->stage.data();
+    return BF_OK;
+}
+int bf_ring_commit(bf_ring *r, int n) {
+    if (!r || n < 0 || n > r->res_n) { g_err = "bf_ring_commit: n exceeds the reservation"; return BF_ERR_ARG; }
+    r->res_n = 0;
+    return bf_ring_push(r, r->stage.data(), n);
 }
 int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_iter, int chain) {
     if (n < 0 || n > r->cap || n > r->pushed) { g_err = "bf_ring_slice: n exceeds the ring's content"; return BF_ERR_ARG; }
@@ -249,6 +263,13 @@ int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_it
 int bf_ring_result(bf_ring *r, int ticket, bf_slice_result *out) {
     if (ticket < 0 || ticket >= r->next_ticket || ticket < r->next_ticket - r->max_pending) { g_err = "bad ticket"; return BF_ERR_ARG; }
     *out = r->res[(size_t)(ticket % r->max_pending)];
+    return BF_OK;
+}
+int bf_ring_seed(bf_ring *r, const bf_model *m) {
+    if (!r || !m) { g_err = "bf_ring_seed: bad arguments"; return BF_ERR_ARG; }
+    memset(&r->prev, 0, sizeof r->prev);
+    r->prev.model = *m;
+    r->have_prev = false;                  // (no noise marks carried over)
     return BF_OK;
 }
 int bf_ring_sync(bf_ring *) { return BF_OK; }

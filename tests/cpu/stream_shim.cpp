@@ -28,7 +28,8 @@ template <class Flow>
 int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint64_t *ts, int scale, int max_iter, int stm_disable,
         int flush, int batch, int local, int lazy, int max_slices, double *models, long long *info, double *uv) {
     est.set_lazy_events(lazy != 0);
-    est.set_device_ring(lazy == 2);          // lazy == 2: the slice ring lives behind the C ABI (bf_ring_*)
+    est.set_device_ring(lazy >= 2);          // lazy == 2: the slice ring lives behind the C ABI (bf_ring_*)
+                                             // lazy == 3: ... and is switched off at n / 3 and on again at 2 n / 3
     est.set_scale(scale);
     est.set_max_iter(max_iter);
     est.set_stm_disable(stm_disable != 0);
@@ -57,6 +58,8 @@ int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint
         ++ns;
     };
     for (int i = 0; i < n; ++i) {
+        if (lazy == 3 && i == n / 3) est.set_device_ring(false);
+        if (lazy == 3 && i == 2 * (n / 3)) est.set_device_ring(true);
         Event e(fr_x[i], fr_y[i], ts[i]);
         if (est.add_event(e)) record(i + 1);
     }

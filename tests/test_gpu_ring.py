@@ -23,12 +23,17 @@ def _host_chain(ctx, fr_x, fr_y, ts, consumed, max_iter, chain, capacity=50000, 
     return out
 
 
-def _ring_chain(ctx, fr_x, fr_y, ts, consumed, max_iter, chain, capacity=50000, span=200_000_000, max_pending=8):
+def _ring_chain(ctx, fr_x, fr_y, ts, consumed, max_iter, chain, capacity=50000, span=200_000_000, max_pending=8, in_place=False):
     ring = bf.Ring(ctx, capacity, max_pending)
     try:
         tickets, fed = [], 0
         for c in consumed:
-            ring.push(fr_x[fed:c], fr_y[fed:c], ts[fed:c])          # only the NEW events
+            if in_place:                                            # written straight into the pinned staging buffer, in two
+                mid = fed + (c - fed) // 3                          # commits, each smaller than its reservation
+                ring.push_in_place(fr_x[fed:mid], fr_y[fed:mid], ts[fed:mid], reserve=32768)
+                ring.push_in_place(fr_x[mid:c], fr_y[mid:c], ts[mid:c], reserve=32768)
+            else:
+                ring.push(fr_x[fed:c], fr_y[fed:c], ts[fed:c])      # only the NEW events
             fed = c
             idx, start = ring_slice(ts, c, capacity, span)
             tickets.append(ring.slice(len(idx), start, 3, max_iter, chain))   # returns at once: nothing waits for the previous slice
@@ -56,6 +61,67 @@ def test_ring_chain_equals_host_driven_chain(ctx240, chain, ring_cluster):
         assert g["rc"] == w["rc"] == 0 and g["iters"] == w["iters"] and g["n_events"] == w["n_events"]
         assert same_model(g["model"], w["model"])
         assert g["dividers"].tobytes() == w["dividers"].tobytes()
+
+
+def test_ring_reserve_commit_equals_push(ctx240):
+    """bf_ring_reserve / bf_ring_commit (what DVS_flow::add_event writes through): same ring content, same chain; a
+    small ring (capacity 30000) so that staging and device ring both wrap; an event outside the sensor is refused at
+    commit and leaves the ring usable."""
+    st = synth.make_stream(240, 180, 1.5e6, 0.3, seed=79, vel=(40.0, -55.0), omega=0.2)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.int64)
+    consumed = list(range(20000, len(ts), 20000))
+    kw = dict(capacity=30000, span=70_000_000, max_pending=len(consumed))
+    want, _ = _ring_chain(ctx240, fr_x, fr_y, ts, consumed, 8, True, **kw)
+    got, _ = _ring_chain(ctx240, fr_x, fr_y, ts, consumed, 8, True, in_place=True, **kw)
+    assert len(got) == len(want) >= 15
+    for w, g in zip(want, got):
+        assert g["iters"] == w["iters"] and g["n_events"] == w["n_events"] and same_model(g["model"], w["model"])
+    ring = bf.Ring(ctx240, 30000, 4)
+    try:
+        with pytest.raises(bf.BfError):
+            ring.push_in_place(np.array([10, 500]), np.array([10, 10]), np.array([1, 2]))
+        assert ring.pushed == 0
+        ring.push_in_place(fr_x[:5000], fr_y[:5000], ts[:5000])
+        assert ring.pushed == 5000
+        with pytest.raises(bf.BfError):
+            ring._chk(ring.lib.bf_ring_commit(ring.h, 1))                  # no reservation open
+    finally:
+        ring.close()
+
+
+def test_ring_seed_continues_a_chain_in_a_new_ring(ctx240):
+    """bf_ring_seed: a ring created in the middle of a stream (DVS_flow after a context was re-created or after the host
+    path handled some slices) starts its chain from the caller's last model, not from ObjectModel()."""
+    st = synth.make_stream(240, 180, 1.5e6, 0.12, seed=78, vel=(-50.0, 45.0), omega=-0.3)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.int64)
+    consumed = list(range(20000, len(ts), 20000))
+    want = _host_chain(ctx240, fr_x, fr_y, ts, consumed, -1, True)
+    k = len(consumed) // 2
+    assert k >= 2
+    ring = bf.Ring(ctx240, 50000, 8)
+    try:
+        lo = max(0, consumed[k] - 50000)
+        ring.push(fr_x[lo:consumed[k]], fr_y[lo:consumed[k]], ts[lo:consumed[k]])   # the window as slice k sees it
+        ring.seed(want[k - 1]["model"])
+        got, fed = [], consumed[k]
+        for c in consumed[k:]:
+            ring.push(fr_x[fed:c], fr_y[fed:c], ts[fed:c])
+            fed = c
+            idx, start = ring_slice(ts, c)
+            got.append(ring.result(ring.slice(len(idx), start, 3, -1, True)))
+    finally:
+        ring.close()
+    for w, g in zip(want[k:], got):
+        assert g["iters"] == w["iters"] and same_model(g["model"], w["model"])
+    # (without the seed the first of these slices starts cold and takes a different number of steps)
+    ring = bf.Ring(ctx240, 50000, 8)
+    try:
+        ring.push(fr_x[lo:consumed[k]], fr_y[lo:consumed[k]], ts[lo:consumed[k]])
+        idx, start = ring_slice(ts, consumed[k])
+        cold = ring.result(ring.slice(len(idx), start, 3, -1, True))
+    finally:
+        ring.close()
+    assert not same_model(cold["model"], want[k]["model"])
 
 
 def test_ring_golden_warm_start_stream(ctx240):

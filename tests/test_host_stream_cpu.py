@@ -193,6 +193,23 @@ def test_device_ring_mode_changes_no_model(hs, config, stm):
         assert np.array_equal(b, want)
 
 
+@pytest.mark.parametrize("stm", [False, True])
+def test_device_ring_switched_off_and_on_mid_stream(hs, stm):
+    """The window lives in ONE of two host rings (152-byte Events, or the device ring's 16-byte records while the slices
+    are cut behind the ABI).  Switching the mode with events in the window moves them across (size, order and the
+    full-buffer quirk preserved), reads the outstanding models back first and rebuilds the device ring when the mode
+    returns: no slice, trigger or model changes."""
+    st = synth.make_stream(240, 180, 1.0e6, 0.2, seed=52, vel=(70.0, -40.0), omega=-0.4)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    a, ia, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=5, lazy=1)
+    p0, s0 = hs.bf_mock_ring_pushed_events(), hs.bf_mock_ring_slices()
+    b, ib, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=5, lazy=3)
+    assert len(a) == len(b) >= 8 and ia.tolist() == ib.tolist()
+    assert np.array_equal(a, b), np.abs(a - b).max()
+    assert 0 < hs.bf_mock_ring_slices() - s0 < len(b)                      # some slices on each side of the switches
+    assert hs.bf_mock_ring_pushed_events() - p0 > 0
+
+
 def test_device_ring_tiny_window_noise(hs):
     """The tiny-window guard's noise marks live behind the ABI in ring mode: later overlapping slices skip the events."""
     rng = np.random.default_rng(3)
