@@ -2020,6 +2020,7 @@ bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
     ok(cudaMalloc(&r->d_res, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
     ok(cudaMemset(r->d_res, 0, (size_t)(max_pending + 1) * sizeof(bf_slice_result)));
     ok(cudaMallocHost(&r->h_res, (size_t)max_pending * sizeof(bf_slice_result)));
+    { cudaFuncAttributes fa; ok(cudaFuncGetAttributes(&fa, bf_ring_build_kernel)); }   // (loads the kernel now, not inside the first slice)
     r->pushes.resize(16);
     for (auto &p : r->pushes) { p.ev = nullptr; p.lo = p.hi = 0; p.open = false; ok(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming)); }
     if (e != cudaSuccess) {

@@ -134,9 +134,11 @@ protected:
     struct Deferred { SliceLog log; int ticket; };
     std::deque<Deferred> deferred_;          // slices enqueued on the device whose models have not been read back yet
     double t_push_ = 0, t_slice_ = 0, t_resolve_ = 0;   // host seconds spent in bf_ring_push / bf_ring_slice / bf_ring_result
+    double t_recompute_ = 0;                            // ... and in recompute() as a whole (device-ring mode)
 public:
     // (BF_TIMING diagnostics of the tool) host time spent inside the ring's three entry points
     void ring_host_seconds(double &push, double &slice, double &resolve) const { push = t_push_; slice = t_slice_; resolve = t_resolve_; }
+    double recompute_host_seconds() const { return t_recompute_; }
 protected:
 
 public:
@@ -209,6 +211,7 @@ public:
     void set_lazy_events(bool v = true) { lazy_events_ = v; update_ring_on(); }
     void set_flow_out(std::ostream *os) { flow_out_ = os; }
     void set_device_ring(bool v = true) { device_ring_ = v; update_ring_on(); }
+    void prepare();   // optional: create the device-side objects now instead of inside the first slice
     bool device_ring_active() const { return ring_on_; }
     ObjectModel get_last_model() { resolve_deferred(); return last_model; }
     ull slices_done() { resolve_deferred(); return slices_done_; }
@@ -250,6 +253,7 @@ protected:
     void run_pending();
     void resolve_deferred();
     void ring_slice(const SliceLog &log, ull start);
+    bool ensure_ring();
 };
 
 template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::migrate_window(bool to_headers) {
@@ -320,7 +324,9 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::recompute() {
             accumulated.push_back(std::move(cur));
         }
     } else if (device_ring_active()) {
+        const auto tr0 = std::chrono::steady_clock::now();
         ring_slice(log, start);
+        t_recompute_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count();
     } else if (batch_ > 1 && stm_disable) {
         // independent slice: snapshot it and minimise later together with its neighbours
         Pending p;
@@ -602,10 +608,9 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::stage_slow(const
     stage_fill_ = 1;
 }
 
-// Default mode on the device-resident ring (include/bf_cuda.h: bf_ring_*).  Per slice the host uploads the events
-// that arrived since the last slice and enqueues "newest n events, local time relative to `start`, warm-started from
-// the previous slice's model ON THE DEVICE"; nothing here waits for the GPU unless the per-slice dump is wanted.
-template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const SliceLog &log, ull start) {
+// Makes sure the device ring exists under the current pooled context; returns true if it had to be (re)built -- it then
+// holds the whole window, staged events included.
+template <size_t MAX_SZ, sll SPAN> bool DVS_flow<MAX_SZ, SPAN>::ensure_ring() {
     auto check = [](int rc, const char *what) {
         if (rc < 0) {
             std::cerr << what << " failed: " << bf_last_error() << std::endl;
@@ -616,24 +621,52 @@ template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const
     // a request that re-creates the pooled context destroys the ring: read the outstanding models back first
     if (ring_ && ring_gen_ == CudaDriver::generation() && !CudaDriver::fits(cap + 64, 1, scale)) resolve_deferred();
     bf_ctx *ctx = CudaDriver::context(cap + 64, 1, scale);
-    const auto tp0 = std::chrono::steady_clock::now();
-    if (!ring_ || ring_gen_ != CudaDriver::generation()) {
-        // (a context re-created for more capacity took its rings with it)
-        stage_drop();
-        ring_ = bf_ring_create(ctx, cap, ring_pending_);
-        if (!ring_) check(-1, "bf_ring_create");
-        ring_gen_ = CudaDriver::generation();
-        // a ring created in the middle of a stream continues the warm-start chain from the host's last model
-        const bf_model seed = last_model.to_pod();
-        check(bf_ring_seed(ring_, &seed), "bf_ring_seed");
-        // everything the window holds, oldest -> newest (the events of this slice included)
-        ring_new_.clear();
-        for (long int i = (long int)hdr_buffer_.size() - 1; i >= 0; i--) ring_new_.push_back(hdr_buffer_[i]);
-        check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
-        ring_new_.clear();
-    } else {
-        check(bf_ring_commit(ring_, stage_fill_), "bf_ring_commit");   // the events that arrived since the last slice
+    if (ring_ && ring_gen_ == CudaDriver::generation()) return false;
+    // (a context re-created for more capacity took its rings with it)
+    stage_drop();
+    ring_ = bf_ring_create(ctx, cap, ring_pending_);
+    if (!ring_) check(-1, "bf_ring_create");
+    ring_gen_ = CudaDriver::generation();
+    // a ring created in the middle of a stream continues the warm-start chain from the host's last model
+    const bf_model seed = last_model.to_pod();
+    check(bf_ring_seed(ring_, &seed), "bf_ring_seed");
+    // everything the window holds, oldest -> newest
+    ring_new_.clear();
+    for (long int i = (long int)hdr_buffer_.size() - 1; i >= 0; i--) ring_new_.push_back(hdr_buffer_[i]);
+    if (!ring_new_.empty()) check(bf_ring_push(ring_, ring_new_.data(), (int)ring_new_.size()), "bf_ring_push");
+    ring_new_.clear();
+    return true;
+}
+
+// Start-up work the first slice would otherwise pay for (pooled context, device ring and its pinned staging buffer).
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::prepare() {
+    if (!ring_on_) {
+        if (gpus_ > 1 || local_) return;   // (the multi-GPU front and OptimizerLocal size their contexts themselves)
+        const int nb = (batch_ > 1 && stm_disable) ? batch_ : 1;
+        CudaDriver::context(((long long)ev_buffer.capacity() + 64) * nb, nb, scale);
+        return;
     }
+    if (ensure_ring()) {
+        if (bf_ring_reserve(ring_, kStageChunk, &stage_) < 0) {
+            std::cerr << "bf_ring_reserve failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+        stage_fill_ = 0; stage_room_ = kStageChunk;
+    }
+}
+
+// Default mode on the device-resident ring (include/bf_cuda.h: bf_ring_*).  Per slice the host uploads the events
+// that arrived since the last slice and enqueues "newest n events, local time relative to `start`, warm-started from
+// the previous slice's model ON THE DEVICE"; nothing here waits for the GPU unless the per-slice dump is wanted.
+template <size_t MAX_SZ, sll SPAN> void DVS_flow<MAX_SZ, SPAN>::ring_slice(const SliceLog &log, ull start) {
+    auto check = [](int rc, const char *what) {
+        if (rc < 0) {
+            std::cerr << what << " failed: " << bf_last_error() << std::endl;
+            std::exit(1);
+        }
+    };
+    const auto tp0 = std::chrono::steady_clock::now();
+    if (!ensure_ring()) check(bf_ring_commit(ring_, stage_fill_), "bf_ring_commit");   // the events that arrived since the last slice
     check(bf_ring_reserve(ring_, kStageChunk, &stage_), "bf_ring_reserve");
     stage_fill_ = 0; stage_room_ = kStageChunk;
     const auto tp1 = std::chrono::steady_clock::now();

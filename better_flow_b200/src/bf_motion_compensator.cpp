@@ -182,6 +182,8 @@ __attribute__((hot)) static int tool_main(int argc, char *argv[]) {
         estimator.set_flow_out(&flow_out);
     }
 
+    estimator.prepare();                  // device context (and slice ring) now, not inside the first slice
+    stamp("device objects created");
     const auto wall0 = std::chrono::steady_clock::now();
     bool final_done = false;
     const size_t flen = strlen(file);
@@ -233,7 +235,7 @@ __attribute__((hot)) static int tool_main(int argc, char *argv[]) {
             estimator.ring_host_seconds(tp, ts, tr);
             if (tp + ts + tr > 0)
                 std::cerr << "[timing] device ring, host seconds inside bf_ring_push " << tp << ", bf_ring_slice " << ts
-                          << ", bf_ring_result (waiting for the GPU) " << tr << std::endl;
+                          << ", bf_ring_result (waiting for the GPU) " << tr << "; ring_slice() as a whole " << estimator.recompute_host_seconds() << std::endl;
             std::cerr << "[timing] processing " << i << " events in " << w << " s = " << double(i) / w / 1e6 << " Mev/s, slices "
                       << estimator.slices_done() << std::endl;
         }
