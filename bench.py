@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--upload-format", default="plain", choices=["plain", "delta"],
                     help="end-to-end path: 8-byte records (default) or 6-byte delta records (25 %% fewer H2D bytes; at 8 GPUs, where four of them "
                          "share one host link, 28.6 instead of 22.7 Gev/s end to end: profiles/r2m_*).  Opt-in: with the 1280x720 configuration on 4 "
-                         "GPUs two of three runs stalled in the delta instance of the kernel (not reproduced on one GPU, unexplained: DESIGN.md 12)")
+                         "GPUs two of three runs stalled in the delta instance of the kernel (not reproduced on one GPU, unexplained: DESIGN.md 7)")
     ap.add_argument("--opt", default="", help="library options key=value[,key=value] (development: A/B of kernel variants)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -908,6 +910,7 @@ struct bf_ctx {
     struct SliceDesc *sl_buf[2] = {nullptr, nullptr};
     int cur = 0;
     int upload_chunks = 32;
+    int upload_delay_us = 0;               // debug: host-side pause on the copy stream before every chunk (emulates a slow host link)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // options
@@ -1259,6 +1262,7 @@ int bf_ctx_set_option(bf_ctx *c, const char *key, long long value) {
     }
     else if (!strcmp(key, "tail_help")) c->tail_help = value ? 1 : 0;
     else if (!strcmp(key, "max_grow")) c->max_grow = (int)std::min<long long>(BF_MAX_GROW, std::max(1LL, value));
+    else if (!strcmp(key, "upload_delay_us")) c->upload_delay_us = (int)std::max(0LL, std::min(value, 1000000LL));
     else if (!strcmp(key, "upload_chunks")) c->upload_chunks = (int)std::min(60LL, std::max(1LL, value));
     else if (!strcmp(key, "ctas_per_sm")) c->ctas_per_sm = (value >= 4 && BF_NT <= 256) ? 4 : (value >= 2 ? 2 : 1);
     else return fail(BF_ERR_ARG, "unknown option '%s'", key);
@@ -1491,6 +1495,10 @@ int bf_batch_launch(bf_ctx *c, int want_events) {
 // batch that the PREVIOUS launch is not reading (two copies, ping-pong), so back-to-back streamed runs
 // overlap the H2D of batch k+1 with the kernel of batch k.  Asynchronous; pair with bf_batch_sync (and
 // do not touch the staging buffer before that).
+static void CUDART_CB upload_pause(void *us) {
+    std::this_thread::sleep_for(std::chrono::microseconds((intptr_t)us));
+}
+
 int bf_batch_run_streamed(bf_ctx *c, int want_events) {
     if (!c) return fail(BF_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
@@ -1525,6 +1533,7 @@ int bf_batch_run_streamed(bf_ctx *c, int want_events) {
         if (s1 <= s0) continue;
         const long long lo = c->h_slices[s0].ev_off;
         const long long hi = c->h_slices[s1 - 1].ev_off + c->h_slices[s1 - 1].n;
+        if (c->upload_delay_us > 0) CU(cudaLaunchHostFunc(c->copy_stream, upload_pause, (void *)(intptr_t)c->upload_delay_us));
         if (hi > lo && delta) {
             // compact upload: the chunk's 6-byte records and block descriptors; the group that takes a slice expands it
             // into the event buffer in its prologue (delta_expand_slice).  DMA only on this stream: a second kernel could
