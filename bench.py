@@ -225,7 +225,8 @@ def class_surface_e2e(device_index):
             return None
         return {"value": out["default_mode"]["value"], "unit": UNIT, "events": len(st), "modes": out,
                 "what": "bf_motion_compensator (DVS_flow class surface), reference default mode: overlapping 50 k-event / 200 ms windows every "
-                        "20 k events, warm-start chain, GD to convergence; events in host memory, add_event loop + all slices + model read-back timed"}
+                        "20 k events, warm-start chain, GD to convergence; events in host memory, device context and slice ring created before the stream "
+                        "(DVS_flow::prepare), add_event loop + all slices + model read-back timed"}
     except Exception as exc:   # the bench line must not depend on this extra
         print("class-surface measurement skipped: %s" % exc, file=sys.stderr)
         return None

@@ -76,6 +76,19 @@ def test_ring_reserve_commit_equals_push(ctx240):
     assert len(got) == len(want) >= 15
     for w, g in zip(want, got):
         assert g["iters"] == w["iters"] and g["n_events"] == w["n_events"] and same_model(g["model"], w["model"])
+    # one commit larger than the ring: only its newest `capacity` events can ever be used
+    res = []
+    for in_place in (False, True):
+        ring = bf.Ring(ctx240, 12000, 4)
+        try:
+            (ring.push_in_place if in_place else ring.push)(fr_x[:30000], fr_y[:30000], ts[:30000])
+            assert ring.pushed == 30000
+            res.append(ring.result(ring.slice(12000, int(ts[18000]), 3, 6, False)))
+        finally:
+            ring.close()
+    w = ctx240.minimize(fr_x[18000:30000][::-1], fr_y[18000:30000][::-1], (ts[18000:30000][::-1] - ts[18000]).astype(np.int32), 3, 6)
+    for g in res:
+        assert g["iters"] == w["iters"] and g["n_events"] == 12000 and same_model(g["model"], w["model"])
     ring = bf.Ring(ctx240, 30000, 4)
     try:
         with pytest.raises(bf.BfError):

@@ -210,6 +210,24 @@ def test_device_ring_switched_off_and_on_mid_stream(hs, stm):
     assert hs.bf_mock_ring_pushed_events() - p0 > 0
 
 
+def test_device_ring_more_new_events_than_one_staging_reservation(hs):
+    """New events go straight into the ring's pinned staging buffer, 32768 at a reservation (bf_ring_reserve / commit).
+    With 45000 new events per slice (only the time trigger of 100 ms could fire earlier) a reservation fills between
+    two slices and is committed and renewed from add_event itself; with the window capacity of 30000 (config 1) a slice
+    even brings more new events than the ring can hold.  Same models, no event uploaded twice."""
+    st = synth.make_stream(240, 180, 1.2e6, 0.2, seed=61, vel=(30.0, 60.0))
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    for config in (0, 1):
+        kw = dict(config=config, ev_refresh=45000, time_refresh_ns=100_000_000, max_iter=4)
+        a, ia, _ = run_host(hs, fr_x, fr_y, ts, lazy=1, **kw)
+        p0 = hs.bf_mock_ring_pushed_events()
+        b, ib, _ = run_host(hs, fr_x, fr_y, ts, lazy=2, **kw)
+        assert len(a) == len(b) >= 4 and ia.tolist() == ib.tolist()
+        assert np.array_equal(a, b)
+        # (the first slice builds the ring from the window: with config 1 that is the newest 30000 of its 45000 events)
+        assert hs.bf_mock_ring_pushed_events() - p0 == len(ts) - (15000 if config == 1 else 0)
+
+
 def test_device_ring_tiny_window_noise(hs):
     """The tiny-window guard's noise marks live behind the ABI in ring mode: later overlapping slices skip the events."""
     rng = np.random.default_rng(3)
