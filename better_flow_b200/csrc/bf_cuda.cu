@@ -1064,7 +1064,7 @@ static int next_tag_base(bf_ctx *c, unsigned *tag_base) {
     return BF_OK;
 }
 
-static int configure(bf_ctx *c, int n_slices, long long n_events = -1) {
+static int configure(bf_ctx *c, int n_slices, long long n_events = -1, int fixed_group = 0) {
     if (n_events < 0) n_events = c->n_events;
     const int want = max_groups(c);
     if (want != c->n_groups_alloc || !c->d_images) {
@@ -1112,6 +1112,11 @@ static int configure(bf_ctx *c, int n_slices, long long n_events = -1) {
 #endif
     }
     pick_launch(c, n_slices, n_events, &c->G, &c->n_groups);
+    if (fixed_group > 0 && c->opt_group <= 0) {
+        // one group of exactly this many CTAs, nobody joins later (LaunchSpec::group)
+        c->G = std::min(c->sms * c->ctas_per_sm, fixed_group);
+        c->n_groups = 1;
+    }
     return BF_OK;
 }
 
@@ -1568,6 +1573,7 @@ struct LaunchSpec {
     const unsigned *ready;
     const bf_slice_result *chain_src; // device record for slices with has_init == 2, or null
     int want_events;
+    int group = 0;                    // > 0: ONE group of this many CTAs from the first iteration on (no tail helping)
     int cluster = 0;                  // > 0: launch the CLUSTER instance with groups = thread-block clusters of this many CTAs
     bf_event *events_w = nullptr;     // compact upload: writable event buffer + records + block table (else null)
     const unsigned short *delta_rec = nullptr;
@@ -1576,7 +1582,7 @@ struct LaunchSpec {
 
 static int launch_spec(bf_ctx *c, const LaunchSpec &L) {
     CU(cudaSetDevice(c->device));
-    int rc = configure(c, L.n_slices, L.n_events);
+    int rc = configure(c, L.n_slices, L.n_events, L.group);
     if (rc != BF_OK) return rc;
     if (L.want_events && !c->d_nxy) {
         CU(cudaMalloc(&c->d_nxy, (size_t)c->max_events * sizeof(double2)));
@@ -2143,6 +2149,13 @@ int bf_ring_slice(bf_ring *r, int n, uint64_t slice_start, int scale, int max_it
     c->launches += 1;
     LaunchSpec L{c->d_events, r->d_desc + slot, r->d_res + slot, 1, (long long)n, nullptr, prev, 0};
     L.cluster = c->ring_cluster;
+    // An independent slice (chain == 0) runs alone on the device: the default launch shape for one slice (16 CTAs, idle
+    // groups joining one per iteration up to 64) spends its first iterations growing.  One group of n / 800 CTAs from the
+    // start: 0.250 instead of 0.303 ms per 50 k-event slice (profiles/r2z_ring_latency_wide_groups.txt).  Chained slices
+    // keep the shape of the host-driven single-slice launch (bf_minimize): the fp64 moments are summed per CTA, another
+    // grouping changes their last bits, and a warm-start chain amplifies that at knife-edge exits -- the ring
+    // chain stays bit-identical to the chain driven through bf_minimize.
+    if (!chain) L.group = (int)std::min<long long>(96, std::max<long long>(16, (n / 800 + 7) / 8 * 8));
     const int rc = launch_spec(c, L);
     if (rc != BF_OK) return rc;
     // (the record stays on the device -- the next slice of a chain reads it there; bf_ring_result fetches on demand)

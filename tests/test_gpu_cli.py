@@ -127,8 +127,14 @@ def test_cli_batch_mode_equals_unbatched(cli, tmp_path):
         out = tmp_path / ("f%d.txt" % batch)
         r = run([cli, "--quiet", "--stm-disable", "--max-iter=10", "--batch=%d" % batch, "--flow-out=%s" % out, str(binf)])
         assert r.returncode == 0, r.stderr[-1500:]
-        outs.append(open(out).read())
-    assert outs[0] == outs[1] and len(outs[0].splitlines()) >= 8
+        outs.append(np.loadtxt(out, ndmin=2))
+    # Unbatched independent slices run one per launch on ONE group of CTAs sized for the slice, batched ones on the batch's
+    # groups: the fp64 gradient moments are summed per CTA, so their last bits depend on the grouping (helpers.same_model).
+    a, b = outs
+    assert a.shape == b.shape and len(a) >= 8
+    whole = np.all(a == np.round(a), axis=0) & np.all(b == np.round(b), axis=0)       # slice number, size, iterations, cnt ...
+    assert whole.sum() >= 3 and np.array_equal(a[:, whole], b[:, whole])
+    assert np.allclose(a, b, rtol=1e-9, atol=0)
 
 
 # ---- warm-start chains, slice by slice ----------------------------------------------------------------------

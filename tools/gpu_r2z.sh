@@ -4,6 +4,5 @@ mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 200 compute-sanitizer --tool memcheck python tools/sanitize_ring.py > gpurun_out/sanitizer_ring_memcheck.log 2>&1; tail -4 gpurun_out/sanitizer_ring_memcheck.log
+bash tools/gpu_r2za.sh | tail -12
 timeout 300 python bench.py > gpurun_out/bench_line.json 2> gpurun_out/bench.err; tail -c 2500 gpurun_out/bench_line.json
-timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_line_reference_arm.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_line_reference_arm.json

@@ -52,6 +52,10 @@ if os.environ.get("BF_PROFILE_PHASES"):
     print("last slice: %d CTAs took part; leader-side CTA cycles -> us:" % len(act))
     print("  " + "  ".join("%s %.1f" % (names[k], lead[k] * clk) for k in (7, 0, 1, 2, 3, 4, 5, 6, 8, 13)) + "  iters %d" % lead[9])
     ctx.set_option("profile", 0)
+if os.environ.get("BF_WIDE_GROUPS"):
+    for G, mg, th in ((32, 2, 1), (32, 1, 0), (48, 1, 0), (64, 1, 0), (96, 1, 0), (24, 3, 1), (16, 4, 1)):
+        chain("group_size %d, max_grow %d, tail_help %d" % (G, mg, th), group_size=G, max_grow=mg, tail_help=th)
+    sys.exit(0)
 for G, mg in ((4, 8), (4, 16), (8, 8), (16, 4), (16, 8), (2, 32)):
     chain("group_size %d, max_grow %d" % (G, mg), group_size=G, max_grow=mg)
 ctx.set_option("group_size", 0); ctx.set_option("max_grow", 8)
