@@ -137,6 +137,29 @@ def test_cli_batch_mode_equals_unbatched(cli, tmp_path):
     assert np.allclose(a, b, rtol=1e-9, atol=0)
 
 
+@pytest.mark.parametrize("extra", [[], ["--stm-disable"]])
+def test_cli_device_ring_equals_host_ring(cli, tmp_path, extra):
+    """The tool's default path (no -o: slices cut on the device, bf_ring_*, events written straight into the ring's
+    staging buffer, models read back late) against --no-device-ring (every window handed over through bf_minimize): same
+    slices, same iteration counts, same models.  Chained slices use the same launch shape on both paths (bit-identical in
+    every run measured, profiles/r2z_cli_timing_fixed_group.txt); independent ones (--stm-disable) run on another CTA
+    grouping on the ring, which moves the last bits of the fp64 moments."""
+    st = synth.make_stream(240, 180, 2.5e6, 0.25, seed=23, vel=(55.0, -35.0), omega=0.3)
+    binf = tmp_path / "s.bin"
+    write_bin(binf, st)
+    outs = []
+    for ring in (True, False):
+        out = tmp_path / ("f%d.txt" % ring)
+        r = run([cli, "--quiet", "--flow-out=%s" % out] + ([] if ring else ["--no-device-ring"]) + extra + [str(binf)])
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(np.loadtxt(out, ndmin=2))
+    a, b = outs
+    assert a.shape == b.shape and len(a) >= 25
+    whole = np.all(a == np.round(a), axis=0) & np.all(b == np.round(b), axis=0)       # slice number, size, iterations, cnt ...
+    assert whole.sum() >= 3 and np.array_equal(a[:, whole], b[:, whole])
+    assert np.allclose(a, b, rtol=1e-9, atol=0)
+
+
 # ---- warm-start chains, slice by slice ----------------------------------------------------------------------
 # A warm-start chain compounds per-slice differences through last_model, so the free-running chain is a weak
 # test of the contract.  Here every slice of a chain is minimised on the GPU from the REFERENCE's own last_model
