@@ -26,6 +26,7 @@ def rd():
     lib = C.CDLL(so)
     for f in (lib.rd_fast, lib.rd_iostream, lib.rd_from_file, lib.rd_prefetch):
         f.restype = C.c_longlong
+    lib.wr_fast.restype = lib.wr_iostream.restype = C.c_double
     return lib
 
 
@@ -155,3 +156,27 @@ def test_fast_record_path_never_diverges_from_iostream(rd, tmp_path):
     assert b[0] == 20000
     same(a, b)
     same(parse(rd, rd.rd_prefetch, path, 30000), b)
+
+
+def test_flow_writer_equals_ostream_byte_for_byte(rd, tmp_path):
+    """EventFile::to_file_uv (the -o file: "t x y 1 v u", 9 decimals) formats with std::to_chars into 1 MB blocks; the
+    file must be what the reference's `ofstream << fixed << setprecision(9)` writes (event_file.h:265-289), including
+    -0, nan, inf, huge and tiny values, and lines that fall on a block boundary."""
+    rng = np.random.default_rng(5)
+    n = 120_000                                                   # > 4 blocks of 1 MB
+    ts = np.sort(rng.integers(0, 2 * 10 ** 12, n)).astype(np.uint64)
+    fx = rng.integers(0, 720, n).astype(np.uint32); fy = rng.integers(0, 1280, n).astype(np.uint32)
+    bu = rng.normal(0, 300, n); bv = rng.normal(0, 1e-4, n)
+    bu[::97] = 0.0; bv[::89] = -0.0; bu[5] = np.nan; bv[6] = np.inf; bu[7] = -np.inf; bv[8] = 1e300; bu[9] = 5e-10; bv[10] = -5e-10
+    bu[11] = 123456789012345678.0; bv[12] = 0.9999999995; bu[13] = 2.5e-9; bv[14] = 0.1234567885
+    bits = rng.integers(0, 2 ** 63, 2000).astype(np.uint64).view(np.float64)
+    bu[1000:3000] = np.where(np.isfinite(bits), bits, 1.0)        # arbitrary bit patterns (incl. subnormals, 1e+-300)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    a, b = tmp_path / "fast.txt", tmp_path / "ios.txt"
+    s_fast = rd.wr_fast(str(a).encode(), C.c_longlong(n), p(ts), p(fx), p(fy), p(bu), p(bv))
+    s_ios = rd.wr_iostream(str(b).encode(), C.c_longlong(n), p(ts), p(fx), p(fy), p(bu), p(bv))
+    da, db = open(a, "rb").read(), open(b, "rb").read()
+    assert len(da) > 4 * (1 << 20) and da == db
+    assert da.splitlines()[0].split() == [("%.9f" % (ts[0] / 1e9)).encode(), str(fy[0]).encode(), str(fx[0]).encode(), b"1",
+                                          ("%.9f" % bv[0]).encode(), ("%.9f" % bu[0]).encode()]
+    print("to_file_uv %.3f s, ostream %.3f s for %d events" % (s_fast, s_ios, n))
