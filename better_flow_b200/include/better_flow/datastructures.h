@@ -16,6 +16,7 @@
 #include <cassert>
 #include <climits>
 #include <cstddef>
+#include <utility>
 #include <vector>
 
 template <class DType> class RingCore {
@@ -133,6 +134,10 @@ public:
         items_.push_back(d);
     }
     void reserve(size_t n) { items_.reserve(n); }
+    void swap(LinearEventCloudTemplate &o) {
+        items_.swap(o.items_);
+        std::swap(x_min, o.x_min); std::swap(y_min, o.y_min); std::swap(x_max, o.x_max); std::swap(y_max, o.y_max);
+    }
     DType &operator[](size_t i) {
         assert(i < items_.size());
         return items_[i];

@@ -89,6 +89,7 @@ protected:
     ull events_done_;
     ull iters_done_;
     bool unsorted_ = false;                  // a timestamp decreased somewhere in the input (see get_accumulated)
+    ull events_added_ = 0;                   // add_event calls (reserve hint for get_accumulated)
     bool generate_pictures_ = false, generate_video_ = false;
     std::string img_prefix_ = "./", video_name_ = "out.avi";
     int video_fps_ = 30;
@@ -168,6 +169,7 @@ public:
         } else {
             ev_buffer.push_back(ev);
         }
+        events_added_++;
         event_diff++;
         if (ev.timestamp < current_slice_time) unsorted_ = true;
         current_slice_time = ev.timestamp;
@@ -740,16 +742,29 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
         std::cout << "FInal buffer contains " << ret.size() << " events." << std::endl;
         return ret;
     }
-    // Per-buffer index "pixel -> positions, oldest first" (counting sort by pixel), built when a buffer is first
-    // scanned and dropped once no earlier buffer can reach it any more: a few buffers are alive at a time.
+    {
+        // every event that was added survives in at most one copy, plus the few that several buffers hold more than
+        // 0.1 ms apart from any same-pixel neighbour cannot exceed what the buffers hold: reserve once instead of doubling
+        ull held = 0;
+        for (auto &buf : accumulated) held += buf.size();
+        ret.reserve((size_t)std::min<ull>(held, events_added_ + events_added_ / 64 + 1024));
+    }
+    // Per-buffer index "pixel -> its events, oldest first" (counting sort by pixel), built when a buffer is first
+    // scanned and dropped once no earlier buffer can reach it any more: a few buffers are alive at a time.  The scan
+    // works on the index alone -- timestamps in pixel order and one "erased" byte per event (the reference's o.t = -1
+    // mark, which only ever decides whether a copy is emitted) -- so the 152-byte copies of the LATER buffers are not
+    // touched at all; each copy is read once, in order, when its own buffer is emitted.
     struct PixelIndex {
-        std::vector<uint32_t> first, pos;    // first[pixel] .. first[pixel + 1] into pos
+        std::vector<uint32_t> first, pos;    // first[pixel] .. first[pixel + 1] into pos / ts
+        std::vector<ull> ts;                 // timestamp of event pos[q]
+        std::vector<uint8_t> dead;           // by position in the buffer
     };
     uint rows = 1, cols = 1;
     for (auto &buf : accumulated)
         for (auto &e : buf) { rows = std::max(rows, e.fr_x + 1); cols = std::max(cols, e.fr_y + 1); }
     std::vector<std::unique_ptr<PixelIndex>> index(accumulated.size());
-    auto index_of = [&](size_t j) -> const PixelIndex & {
+    std::vector<uint32_t> fill;
+    auto index_of = [&](size_t j) -> PixelIndex & {
         if (!index[j]) {
             auto &buf = accumulated[j];
             std::unique_ptr<PixelIndex> ix(new PixelIndex);
@@ -757,35 +772,49 @@ template <size_t MAX_SZ, sll SPAN> LinearEventCloudTemplate<Event> DVS_flow<MAX_
             for (size_t k = 0; k < buf.size(); ++k) ix->first[(size_t)buf[k].fr_x * cols + buf[k].fr_y + 1] += 1;
             for (size_t p = 1; p < ix->first.size(); ++p) ix->first[p] += ix->first[p - 1];
             ix->pos.resize(buf.size());
-            std::vector<uint32_t> fill(ix->first.begin(), ix->first.end() - 1);
-            for (size_t k = 0; k < buf.size(); ++k) ix->pos[fill[(size_t)buf[k].fr_x * cols + buf[k].fr_y]++] = (uint32_t)k;
+            ix->ts.resize(buf.size());
+            ix->dead.assign(buf.size(), 0);
+            fill.assign(ix->first.begin(), ix->first.end() - 1);
+            for (size_t k = 0; k < buf.size(); ++k) {
+                const uint32_t q = fill[(size_t)buf[k].fr_x * cols + buf[k].fr_y]++;
+                ix->pos[q] = (uint32_t)k;
+                ix->ts[q] = buf[k].timestamp;
+            }
             index[j] = std::move(ix);
         }
         return *index[j];
     };
+    std::vector<ull> starts(accumulated.size(), 0);      // timestamp of every buffer's first (oldest) copy
+    for (size_t j = 0; j < accumulated.size(); ++j)
+        if (accumulated[j].size() > 0) starts[j] = accumulated[j][0].timestamp;
     for (ull i = 0; i < accumulated.size(); ++i) {
         std::cout << "\tBuffer: " << i << "\n";
         auto &buf = accumulated[i];
-        for (auto &e : buf) {
-            if (e.t == -1) continue;
+        const uint8_t *dead_i = index[i] ? index[i]->dead.data() : nullptr;   // (nobody looked into this buffer: nothing erased)
+        for (size_t k = 0; k < buf.size(); ++k) {
+            Event &e = buf[k];
+            if (e.t == -1 || (dead_i && dead_i[k])) continue;
             for (ull j = i + 1; j < accumulated.size(); ++j) {
                 // buffers are oldest -> newest copies of a ring whose oldest timestamp never decreases: once a
                 // later buffer STARTS after e, neither it nor any buffer after it holds a candidate (o - e <= 0)
                 if (accumulated[j].size() == 0) continue;
-                if (accumulated[j][0] - e > 0) break;
-                const PixelIndex &ix = index_of(j);
+                if (sll(starts[j]) - sll(e.timestamp) > 0) break;
+                PixelIndex &ix = index_of(j);
                 const size_t pixel = (size_t)e.fr_x * cols + e.fr_y;
                 for (uint32_t q = ix.first[pixel]; q < ix.first[pixel + 1]; ++q) {
-                    Event &o = accumulated[j][ix.pos[q]];
-                    if (o - e > 0) continue;      // newer than e: the reference's scan has stopped by then
-                    if (o.t == -1) continue;
-                    if (e != o) continue;
-                    o.t = -1;
+                    const ull o_ts = ix.ts[q];
+                    if (sll(o_ts) - sll(e.timestamp) > 0) continue;      // newer than e: the reference's scan has stopped by then
+                    // e != o (event.h:40-45) with the pixel equal and o not newer: closer than 0.1 ms or not
+                    if (e.timestamp - o_ts >= 100000) continue;
+                    // (a copy whose local time is the reference's mark value -1 is skipped by its scan as well)
+                    if (ix.dead[ix.pos[q]] || accumulated[j][ix.pos[q]].t == -1) continue;
+                    ix.dead[ix.pos[q]] = 1;
                 }
             }
             ret.push_back(e);
         }
         index[i].reset();
+        LinearEventCloudTemplate<Event>().swap(buf);   // (done with this copy: later buffers only look forward)
     }
     std::cout << "FInal buffer contains " << ret.size() << " events." << std::endl;
     return ret;

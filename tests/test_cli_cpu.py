@@ -152,3 +152,45 @@ def test_out_of_order_input_still_equals_the_reference_tool(mock_cli, tmp_path):
     assert ref.returncode == 0 and new.returncode == 0, (ref.stderr[-500:], new.stderr[-1500:])
     assert open(o_ref, "rb").read() == open(o_new, "rb").read() and os.path.getsize(o_ref) > 100000
     assert _stable(ref.stdout, o_ref, txt) == _stable(new.stdout, o_new, txt)
+
+
+def test_aggregation_of_bursty_pixels_over_many_buffers_equals_the_reference_tool(mock_cli, tmp_path):
+    """-o keeps, of the copies the overlapping buffers hold, the first one and drops from LATER buffers every copy of the
+    same pixel that is not newer and closer than 0.1 ms (dvs_flow.h:350-389, event.h:40-45).  Hot pixels that fire in
+    bursts (gaps on both sides of 0.1 ms, exactly 0.1 ms, equal timestamps) over a dozen overlapping buffers: the
+    indexed scan here must drop exactly what the reference's nested scan drops (which copy of an event survives decides
+    which slice's flow the file reports for it) -- byte-identical files."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/bf_motion_compensator_ref not built (no /root/reference here)")
+    import numpy as np
+    from better_flow_b200 import synth
+    st = synth.make_stream(240, 180, 0.4e6, 0.04, seed=31, vel=(60.0, 20.0))
+    rng = np.random.default_rng(8)
+    hot = [(int(rng.integers(20, 220)), int(rng.integers(20, 160))) for _ in range(24)]
+    bx, by, bt = [], [], []
+    for _ in range(1300):
+        x, y = hot[int(rng.integers(0, len(hot)))]
+        t0 = int(rng.integers(0, 39_000_000))
+        gaps = rng.choice([0, 1, 40_000, 99_999, 100_000, 100_001, 150_000, 30_000], size=3)
+        t = t0
+        for g in [0] + list(gaps):
+            t += int(g)
+            bx.append(x); by.append(y); bt.append(t)
+    t_all = np.concatenate([st.t_ns, np.array(bt, dtype=np.int64)])
+    order = np.argsort(t_all, kind="stable")
+    st.x = np.concatenate([st.x, np.array(bx, dtype=st.x.dtype)])[order]
+    st.y = np.concatenate([st.y, np.array(by, dtype=st.y.dtype)])[order]
+    st.p = np.concatenate([st.p, np.ones(len(bt), dtype=st.p.dtype)])[order]
+    st.t_ns = t_all[order]
+    txt = tmp_path / "events.txt"
+    st.to_text(str(txt))
+    o_ref, o_new = tmp_path / "ref_uv.txt", tmp_path / "new_uv.txt"
+    flags = ["--refresh-event-count=1800"]
+    ref = subprocess.run([REF_CLI] + flags + ["-o", str(o_ref), str(txt)], capture_output=True, text=True, timeout=900)
+    new = subprocess.run([mock_cli] + flags + ["-o", str(o_new), str(txt)], capture_output=True, text=True, timeout=900)
+    assert ref.returncode == 0 and new.returncode == 0, (ref.stderr[-500:], new.stderr[-1500:])
+    n_buffers = sum(1 for l in new.stdout.splitlines() if l.startswith("\tBuffer: "))
+    kept = len(open(o_new, "rb").read().splitlines())
+    assert n_buffers >= 12 and kept == len(st)                    # (every event is emitted once, from the first buffer that holds it)
+    assert open(o_ref, "rb").read() == open(o_new, "rb").read()
+    assert _stable(ref.stdout, o_ref, txt) == _stable(new.stdout, o_new, txt)
