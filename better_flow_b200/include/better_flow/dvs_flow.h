@@ -156,7 +156,10 @@ public:
           scale(3), stm_disable(false), batch_(1), gpus_(1), local_(false), quiet_(false), flow_out_(nullptr), slices_done_(0), events_done_(0),
           iters_done_(0), hdr_buffer_(capacity, span) {}
 
-    ~DVS_flow() {}
+    ~DVS_flow() {
+        // the device ring belongs to the pooled context and would otherwise live until that is destroyed
+        if (ring_ && ring_gen_ == CudaDriver::generation()) bf_ring_destroy(ring_);
+    }
 
     // The per-event part is small and inlined into the caller's loop; the slice itself is not.
     __attribute__((always_inline)) inline bool add_event(Event &ev) {

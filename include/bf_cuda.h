@@ -300,7 +300,9 @@ int bf_color_time_img(bf_ctx *c, int n, const double *pr_x, const double *pr_y, 
  *   bf_ring_push    appends only the NEW events (absolute timestamps, 16-byte records) -- asynchronous H2D;
  *   bf_ring_reserve / bf_ring_commit   the same without the staging copy: `reserve` hands out room for up to n events
  *                   in the ring's pinned staging buffer (waiting for earlier copies that still read that part), the
- *                   caller writes its events there as they arrive, `commit(m <= n)` checks and sends the first m;
+ *                   caller writes its events there as they arrive, `commit(m <= n)` checks and sends the first m (a
+ *                   refused commit leaves the reservation open; a new reservation replaces an open one, whose events
+ *                   are then not sent; bf_ring_push is refused while a reservation is open);
  *   bf_ring_slice   enqueues "minimise the newest n events, local time = timestamp - slice_start"
  *                   (OptimizerRolling::set_cloud / set_time / [set_model] / run, optimizer_rolling.h:236-299,48-125):
  *                   a small kernel cuts the packed newest->oldest slice out of the ring (the order of
