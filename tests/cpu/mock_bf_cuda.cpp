@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/bf_cuda.h"
@@ -32,10 +33,12 @@ struct MockSlice {
     bf_slice_result res;
     std::vector<double> pr;     // pr_x | pr_y | nx | ny
 };
+struct bf_ring;
 struct bf_ctx {
     int rows, cols;
     std::vector<MockSlice> batch;
     long long launches = 0;
+    std::vector<bf_ring *> rings;         // destroyed with the context, as in the library
 };
 static std::string g_err;
 static long long g_minimize_calls = 0, g_batch_runs = 0;
@@ -101,7 +104,12 @@ bf_ctx *bf_ctx_create(int rows, int cols, int, long long, int) {
     c->rows = rows; c->cols = cols;
     return c;
 }
-void bf_ctx_destroy(bf_ctx *c) { delete c; }
+void bf_ring_destroy(bf_ring *r);
+void bf_ctx_destroy(bf_ctx *c) {
+    if (!c) return;
+    while (!c->rings.empty()) bf_ring_destroy(c->rings.back());   // (each removes itself from the list)
+    delete c;
+}
 int bf_ctx_set_option(bf_ctx *, const char *, long long) { return BF_OK; }
 long long bf_ctx_get_option(bf_ctx *, const char *) { return 0; }
 
@@ -206,9 +214,15 @@ bf_ring *bf_ring_create(bf_ctx *c, long long capacity, int max_pending) {
     r->ring.resize((size_t)capacity);
     r->res.resize((size_t)max_pending);
     memset(&r->prev, 0, sizeof r->prev);
+    c->rings.push_back(r);
     return r;
 }
-void bf_ring_destroy(bf_ring *r) { delete r; }
+void bf_ring_destroy(bf_ring *r) {
+    if (!r) return;
+    auto &v = r->c->rings;
+    v.erase(std::remove(v.begin(), v.end(), r), v.end());
+    delete r;
+}
 long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
 int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
     if (g_null) { r->pushed += n; g_ring_pushes += n; return BF_OK; }   // host-overhead timing

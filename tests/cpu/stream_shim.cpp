@@ -30,6 +30,8 @@ int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint
     est.set_lazy_events(lazy != 0);
     est.set_device_ring(lazy >= 2);          // lazy == 2: the slice ring lives behind the C ABI (bf_ring_*)
                                              // lazy == 3: ... and is switched off at n / 3 and on again at 2 n / 3
+                                             // lazy == 4: ... and another user of the pooled context re-creates it at n / 2
+                                             //            (the ring and its staging buffer are gone from one event to the next)
     est.set_scale(scale);
     est.set_max_iter(max_iter);
     est.set_stm_disable(stm_disable != 0);
@@ -60,6 +62,10 @@ int run(Flow &est, int n, const uint32_t *fr_x, const uint32_t *fr_y, const uint
     for (int i = 0; i < n; ++i) {
         if (lazy == 3 && i == n / 3) est.set_device_ring(false);
         if (lazy == 3 && i == 2 * (n / 3)) est.set_device_ring(true);
+        if (lazy == 4 && i == n / 2) {
+            est.get_last_model();                                  // (settle the outstanding tickets first, as such a user must)
+            CudaDriver::context(4000000, 3, scale);                // does not fit the pooled context: destroyed and re-created
+        }
         Event e(fr_x[i], fr_y[i], ts[i]);
         if (est.add_event(e)) record(i + 1);
     }

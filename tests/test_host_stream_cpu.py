@@ -210,6 +210,20 @@ def test_device_ring_switched_off_and_on_mid_stream(hs, stm):
     assert hs.bf_mock_ring_pushed_events() - p0 > 0
 
 
+@pytest.mark.parametrize("stm", [False, True])
+def test_device_ring_survives_a_recreated_context(hs, stm):
+    """Another user of the pooled context asks for more capacity in the middle of the stream: the context is destroyed
+    and re-created, and the ring and the pinned staging buffer add_event was writing into go with it.  The events that
+    arrive before the next slice must not be written into the freed buffer (per-event generation check); the next slice
+    rebuilds the ring from the host's window and seeds the chain with the host's last model: no model changes."""
+    st = synth.make_stream(240, 180, 1.0e6, 0.2, seed=53, vel=(-45.0, 65.0), omega=0.2)
+    fr_x, fr_y, ts = st.y, st.x, st.t_ns.astype(np.uint64)
+    a, ia, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=5, lazy=1)
+    b, ib, _ = run_host(hs, fr_x, fr_y, ts, stm_disable=stm, max_iter=5, lazy=4)
+    assert len(a) == len(b) >= 8 and ia.tolist() == ib.tolist()
+    assert np.array_equal(a, b), np.abs(a - b).max()
+
+
 def test_device_ring_more_new_events_than_one_staging_reservation(hs):
     """New events go straight into the ring's pinned staging buffer, 32768 at a reservation (bf_ring_reserve / commit).
     With 45000 new events per slice (only the time trigger of 100 ms could fire earlier) a reservation fills between
