@@ -227,7 +227,7 @@ long long bf_ring_pushed(bf_ring *r) { return r ? r->pushed : 0; }
 int bf_ring_push(bf_ring *r, const bf_ring_event *ev, int n) {
     if (g_null) { r->pushed += n; g_ring_pushes += n; return BF_OK; }   // host-overhead timing
     for (int i = 0; i < n; ++i) {
-        if (ev[i].fr_x >= r->c->rows || (ev[i].fr_y & 0x7fffu) >= r->c->cols) { g_err = "event outside the sensor"; return BF_ERR_ARG; }
+        if ((int)ev[i].fr_x >= r->c->rows || (int)(ev[i].fr_y & 0x7fffu) >= r->c->cols) { g_err = "event outside the sensor"; return BF_ERR_ARG; }
         r->ring[(size_t)(r->pushed % r->cap)] = ev[i];
         r->pushed += 1;
     }
